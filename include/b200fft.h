@@ -1,0 +1,141 @@
+/*
+ * b200fft.h -- C ABI of the B200-native FFT / convolution engine (libb200fft.so).
+ *
+ * This is the drop-in boundary for the hot path of vlazzarini/opencl_fft. Everything is
+ * extern "C": opaque handles, plain pointers, ints. The reference's own C++ classes
+ * (include/cl_fft.h, include/cl_conv.h, include/cl_dconv.h -- same public interface as the
+ * reference's headers of the same name) are thin inline wrappers over these entry points, so
+ * test_cfft.cpp, test_rfft.cpp and csound/opcode.cpp compile unchanged; any other host language
+ * binds the same symbols (INTEGRATION.md shows the ctypes binding shipped in opencl_fft_b200/).
+ *
+ * Each entry point names the reference interface it replaces (file:line under the reference
+ * repository). Semantics -- scaling, packing, ring order, quirks Q1..Q6, Q9, Q12 of SURVEY.md --
+ * are the reference's; where the reference is undefined or broken (Q10, Q11, Q13, Q15) the
+ * behaviour is defined here and documented at the function.
+ *
+ * Conventions
+ *   - return value: 0 = success (== CL_SUCCESS), > 0 = B2F_ERR_* (the reference's callers test
+ *     `err > 0`, test_cfft.cpp:41, so positive codes make those checks live). b2f_error_string()
+ *     maps a code to text. There is NO CPU fallback: without a CUDA device every create fails.
+ *   - "host" entry points take host pointers and are synchronous (they return after the result
+ *     is in the caller's buffer), like the reference's blocking reads (cl_fft.cpp:158).
+ *   - "dev" entry points take device pointers and a cudaStream_t (passed as void*) and only
+ *     enqueue work; this is the batched, HBM-resident path the roofline numbers are measured on.
+ *   - complex data is interleaved float32 (re, im) == std::complex<float> == OpenCL float2.
+ *   - batch / channels: the reference has one object per transform / channel; a handle here
+ *     carries `max_batch` transforms or `channels` independent convolver states and runs them in
+ *     one launch. batch = channels = 1 is exactly the reference object.
+ */
+#ifndef B200FFT_H
+#define B200FFT_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define B2F_OK 0
+#define B2F_ERR_NO_DEVICE 1      /* no CUDA device / bad ordinal (cf. CL_DEVICE_NOT_FOUND) */
+#define B2F_ERR_INVALID_VALUE 2  /* bad size / NULL pointer (cf. CL_INVALID_VALUE) */
+#define B2F_ERR_UNSUPPORTED 3    /* size outside what this build implements */
+#define B2F_ERR_ALLOC 4          /* device or pinned-host allocation failed */
+#define B2F_ERR_CUDA 5           /* a CUDA call / launch failed; see b2f_last_cuda_error() */
+#define B2F_ERR_BATCH 6          /* batch larger than the handle's max_batch */
+
+const char *b2f_error_string(int code);
+/* text of the last CUDA runtime error seen by the calling thread's most recent failing call */
+const char *b2f_last_cuda_error(void);
+/* library version string, e.g. "b200fft 0.1 (sm_100a)" */
+const char *b2f_version(void);
+
+/* ---- devices (replaces clGetDeviceIDs / clGetDeviceInfo as used at test_cfft.cpp:31-38,
+ *      csound/opcode.cpp:57-61) ------------------------------------------------------------- */
+int b2f_device_count(int *count);
+int b2f_device_name(int device, char *buf, size_t buflen);
+
+/* ---- complex FFT: cl_fft::Clcfft (cl_fft.h:29-70, cl_fft.cpp:44-161) ----------------------
+ * N: power of two, 2 <= N <= 65536 (the reference's int32 index math overflows above, Q13).
+ * fwd != 0: X[k] = (1/N) sum x[n] exp(-2 pi i k n / N)   (scaled, cl_fft.cpp:39-40)
+ * fwd == 0: x[n] = sum X[k] exp(+2 pi i k n / N)         (unscaled)                            */
+typedef struct b2f_cfft b2f_cfft;
+int b2f_cfft_create(b2f_cfft **plan, int device, int N, int fwd, int max_batch);
+int b2f_cfft_destroy(b2f_cfft *plan);
+/* Clcfft::transform (cl_fft.cpp:153-161): in place on `batch` consecutive N-point host arrays */
+int b2f_cfft_exec_host(b2f_cfft *plan, float *c, int batch);
+/* device-resident: in/out [batch][N] complex, may alias; asynchronous on `stream` */
+int b2f_cfft_exec_dev(b2f_cfft *plan, const void *d_in, void *d_out, int batch, void *stream);
+
+/* ---- real FFT: cl_fft::Clrfft (cl_fft.h:74-111, cl_fft.cpp:208-296) -----------------------
+ * size: number of real points, power of two, 4 <= size <= 131072; N = size/2 complex bins.
+ * forward output: c[0] = (X[0], X[size/2]) / size packed; c[k] = 2 X[k] / size;
+ * c[size/4] is the conjugate of that (the reference's split skips it, Q3). Inverse undoes it. */
+typedef struct b2f_rfft b2f_rfft;
+int b2f_rfft_create(b2f_rfft **plan, int device, int size, int fwd, int max_batch);
+int b2f_rfft_destroy(b2f_rfft *plan);
+/* Clrfft::transform(c, r) (cl_fft.cpp:267-296). c: size/2 complex, r: size reals, per transform,
+ * `batch` of each back to back. r == (float*)c is the in-place form (cl_fft.h:105-110).
+ * forward: reads r, writes c. inverse: reads c, writes r AND overwrites c with the same reals
+ * (the reference's c is its transfer buffer, cl_fft.cpp:290-293). */
+int b2f_rfft_exec_host(b2f_rfft *plan, float *c, float *r, int batch);
+/* device-resident: forward d_in = [batch][size] float, d_out = [batch][size/2] complex;
+ * inverse the other way round; may alias; asynchronous on `stream` */
+int b2f_rfft_exec_dev(b2f_rfft *plan, const void *d_in, void *d_out, int batch, void *stream);
+
+/* ---- partitioned convolution: cl_conv::Clpconv (cl_conv.h:124-188, cl_conv.cpp:140-548) ----
+ * cvs: impulse-response length, pts: partition size (power of two). nparts = cvs / pts
+ * TRUNCATING (cl_conv.cpp:143, Q4). `channels` independent convolvers (own IR, own delay line,
+ * own overlap tail), laid out channel-major in every buffer.
+ * The reference's optional host-memory constructor arguments (cl_conv.h:156-158) are dead code
+ * there (Q15) and have no counterpart. */
+typedef struct b2f_pconv b2f_pconv;
+int b2f_pconv_create(b2f_pconv **h, int device, int cvs, int pts, int channels);
+int b2f_pconv_destroy(b2f_pconv *h);
+int b2f_pconv_nparts(const b2f_pconv *h);
+/* zero the delay line, the overlap tail and the ring positions (IR spectra are kept) */
+int b2f_pconv_reset(b2f_pconv *h);
+/* Clpconv::push_ir (cl_conv.cpp:353-388). ir: per channel nparts*pts floats, channel c starting
+ * at ir + c*ir_stride (ir_stride in floats; pass cvs for back-to-back IRs). */
+int b2f_pconv_push_ir_host(b2f_pconv *h, const float *ir, size_t ir_stride);
+int b2f_pconv_push_ir_dev(b2f_pconv *h, const void *d_ir, size_t ir_stride, void *stream);
+/* Clpconv::convolution(out, in) (cl_conv.cpp:393-458): one block of pts samples per channel.
+ * in/out: [channels][pts] floats. */
+int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in);
+int b2f_pconv_process_dev(b2f_pconv *h, void *d_out, const void *d_in, void *stream);
+/* Clpconv::convolution(out, in1, in2) (cl_conv.cpp:460-548): time-varying; in2's block is
+ * transformed into the IR ring at the descending write position (Q12). */
+int b2f_pconv_process_tv_host(b2f_pconv *h, float *out, const float *in1, const float *in2);
+int b2f_pconv_process_tv_dev(b2f_pconv *h, void *d_out, const void *d_in1, const void *d_in2, void *stream);
+/* white-box access for parity tests: copy the frequency-domain delay line (`which` = 1, the
+ * reference's spec1) or the IR spectra (`which` = 2, spec2) of one channel to the host,
+ * nparts*pts complex values in the reference's frame order. */
+int b2f_pconv_read_spectra(b2f_pconv *h, int which, int channel, float *dst);
+
+/* ---- direct convolution: cl_conv::Cldconv (cl_dconv.h:17-66, cl_dconv.cpp:46-153) ----------
+ * y[t] = sum_{c < irsize} ir[c] x[t-1-c]: the exact linear convolution delayed by ONE sample,
+ * as the reference computes it (Q9). State starts at zero (the reference leaves it
+ * uninitialised, Q11). When irsize % vsize != 0 the reference's ring write is broken (Q10);
+ * here the stream semantics above simply continue to hold. */
+typedef struct b2f_dconv b2f_dconv;
+int b2f_dconv_create(b2f_dconv **h, int device, int irsize, int vsize, int channels, int max_blocks);
+int b2f_dconv_destroy(b2f_dconv *h);
+int b2f_dconv_reset(b2f_dconv *h);
+/* Cldconv::push_ir (cl_dconv.cpp:150-153): irsize floats per channel */
+int b2f_dconv_push_ir_host(b2f_dconv *h, const float *ir, size_t ir_stride);
+int b2f_dconv_push_ir_dev(b2f_dconv *h, const void *d_ir, size_t ir_stride, void *stream);
+/* Cldconv::convolution(out, in) (cl_dconv.cpp:109-132), `nblocks` consecutive blocks of vsize
+ * samples per channel in one call (nblocks = 1 is the reference call).
+ * in/out: [channels][nblocks*vsize] floats. */
+int b2f_dconv_process_host(b2f_dconv *h, float *out, const float *in, int nblocks);
+int b2f_dconv_process_dev(b2f_dconv *h, void *d_out, const void *d_in, int nblocks, void *stream);
+/* Cldconv::convolution(out, in1, in2) (cl_dconv.cpp:134-148): in2's block is written into the
+ * coefficient ring at the delay line's write position before the block is computed (Q12).
+ * One block per call. in1/in2/out: [channels][vsize]. */
+int b2f_dconv_process_tv_host(b2f_dconv *h, float *out, const float *in1, const float *in2);
+int b2f_dconv_process_tv_dev(b2f_dconv *h, void *d_out, const void *d_in1, const void *d_in2, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FFT_H */

@@ -1,0 +1,876 @@
+// capi.cu -- implementation of the C ABI declared in include/b200fft.h.
+//
+// Host-side responsibilities only: validating sizes, building twiddle tables in double precision
+// exactly as the reference does (cl_fft.cpp:86-91, 233-238; cl_conv.cpp:263-287), owning device
+// state, staging host buffers through pinned memory, and launching the sm_100a kernels in
+// fft_kernels.cuh / fft_large.cuh / pconv_kernels.cuh / dconv_kernels.cuh. There is deliberately
+// no CPU implementation behind these entry points: if CUDA is unavailable every create fails.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fft.h"
+#include "dconv_kernels.cuh"
+#include "fft_kernels.cuh"
+#include "fft_large.cuh"
+#include "pconv_kernels.cuh"
+
+using namespace b2f;
+
+// ---- error plumbing -------------------------------------------------------------------------------
+static thread_local std::string g_cuda_err = "";
+
+static int cuda_fail(cudaError_t e, const char *where) {
+  g_cuda_err = std::string(where) + ": " + cudaGetErrorString(e);
+  (void)cudaGetLastError();  // clear the sticky-less error state
+  if (e == cudaErrorMemoryAllocation) return B2F_ERR_ALLOC;
+  if (e == cudaErrorNoDevice || e == cudaErrorInvalidDevice || e == cudaErrorInsufficientDriver)
+    return B2F_ERR_NO_DEVICE;
+  return B2F_ERR_CUDA;
+}
+#define CK(call)                                       \
+  do {                                                 \
+    cudaError_t e_ = (call);                           \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+extern "C" const char *b2f_error_string(int code) {
+  switch (code) {
+    case B2F_OK: return "Success!";
+    case B2F_ERR_NO_DEVICE: return "CUDA device not found";
+    case B2F_ERR_INVALID_VALUE: return "Invalid value";
+    case B2F_ERR_UNSUPPORTED: return "Size not supported by this build";
+    case B2F_ERR_ALLOC: return "Memory allocation failure";
+    case B2F_ERR_CUDA: return "CUDA runtime failure";
+    case B2F_ERR_BATCH: return "Batch exceeds the plan's max_batch";
+    default: return "Unknown error";
+  }
+}
+extern "C" const char *b2f_last_cuda_error(void) { return g_cuda_err.c_str(); }
+extern "C" const char *b2f_version(void) { return "b200fft 0.1 (sm_100a)"; }
+
+extern "C" int b2f_device_count(int *count) {
+  if (!count) return B2F_ERR_INVALID_VALUE;
+  *count = 0;
+  CK(cudaGetDeviceCount(count));
+  return *count > 0 ? B2F_OK : B2F_ERR_NO_DEVICE;
+}
+extern "C" int b2f_device_name(int device, char *buf, size_t buflen) {
+  if (!buf || buflen == 0) return B2F_ERR_INVALID_VALUE;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  snprintf(buf, buflen, "%s", prop.name);
+  return B2F_OK;
+}
+
+static int ilog2_exact(int n) {
+  if (n <= 0 || (n & (n - 1))) return -1;
+  int l = 0;
+  while ((1 << l) < n) l++;
+  return l;
+}
+static int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (device < 0 || device >= n) return B2F_ERR_NO_DEVICE;
+  CK(cudaSetDevice(device));
+  return B2F_OK;
+}
+
+// ---- twiddle tables ---------------------------------------------------------------------------------
+static const double kPI = 3.141592653589793;  // cl_fft.h:24
+
+// entry q of the reference's N-entry table (cl_fft.cpp:86-91), forward sign; the inverse is its conjugate
+static inline float2 ref_twiddle(long long q, int N) {
+  float2 w;
+  w.x = (float)cos(q * 2 * kPI / N);
+  w.y = (float)(-1.f * sin(q * 2 * kPI / N));
+  return w;
+}
+// pass twiddles of the in-shared-memory engine: for pass p >= 1, rows r = 1..R-1, columns k < NS:
+// W_N^(r * k * N / (NS * R)), i.e. entries of the reference's table at that index
+static std::vector<float2> make_pass_twiddles(int logn) {
+  Sched s = sched_for(logn);
+  const int N = 1 << logn;
+  std::vector<float2> tw((size_t)sched_tw_total(s) + 1);
+  for (int p = 1; p < s.npass; p++) {
+    const int R = s.radix[p], NS = sched_stride(s, p), off = sched_tw_offset(s, p);
+    const int step = N / (NS * R);
+    for (int r = 1; r < R; r++)
+      for (int k = 0; k < NS; k++) tw[off + (r - 1) * NS + k] = ref_twiddle((long long)r * k * step, N);
+  }
+  return tw;
+}
+// split twiddles w2[i] = exp(-i pi i / N) (cl_fft.cpp:233-238, forward sign), N entries
+static std::vector<float2> make_split_twiddles(int N) {
+  std::vector<float2> w(N);
+  for (int i = 0; i < N; i++) {
+    w[i].x = (float)cos(i * kPI / N);
+    w[i].y = (float)(-1.f * sin(i * kPI / N));
+  }
+  return w;
+}
+static int upload(const std::vector<float2> &h, float2 **d) {
+  CK(cudaMalloc((void **)d, h.size() * sizeof(float2)));
+  CK(cudaMemcpy(*d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  return B2F_OK;
+}
+
+// ---- kernel dispatch ----------------------------------------------------------------------------------
+template <class K>
+static int set_smem(K kernel, int bytes) {
+  if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return B2F_OK;
+}
+
+template <int LOGN>
+static int launch_cfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, int batch, float scale,
+                         cudaStream_t st) {
+  using B = BatchGeom<LOGN>;
+  const int grid = (batch + B::TPB - 1) / B::TPB;
+  if (inv) {
+    int rc = set_smem(cfft_kernel<LOGN, true>, B::SMEM_BYTES);
+    if (rc) return rc;
+    cfft_kernel<LOGN, true><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, batch, scale);
+  } else {
+    int rc = set_smem(cfft_kernel<LOGN, false>, B::SMEM_BYTES);
+    if (rc) return rc;
+    cfft_kernel<LOGN, false><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, batch, scale);
+  }
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
+template <int LOGN>
+static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *w2, int batch,
+                         cudaStream_t st) {
+  using B = BatchGeom<LOGN>;
+  const int grid = (batch + B::TPB - 1) / B::TPB;
+  if (inv) {
+    int rc = set_smem(rfft_inv_kernel<LOGN>, B::SMEM_BYTES);
+    if (rc) return rc;
+    rfft_inv_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, w2, batch);
+  } else {
+    int rc = set_smem(rfft_fwd_kernel<LOGN>, B::SMEM_BYTES);
+    if (rc) return rc;
+    rfft_fwd_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, w2, batch);
+  }
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
+
+#define B2F_DISPATCH_LOGN(logn, CALL)  \
+  switch (logn) {                      \
+    case 1: return CALL(1);            \
+    case 2: return CALL(2);            \
+    case 3: return CALL(3);            \
+    case 4: return CALL(4);            \
+    case 5: return CALL(5);            \
+    case 6: return CALL(6);            \
+    case 7: return CALL(7);            \
+    case 8: return CALL(8);            \
+    case 9: return CALL(9);            \
+    case 10: return CALL(10);          \
+    case 11: return CALL(11);          \
+    case 12: return CALL(12);          \
+    case 13: return CALL(13);          \
+    case 14: return CALL(14);          \
+    default: return B2F_ERR_UNSUPPORTED; \
+  }
+
+static int launch_cfft(int logn, bool inv, const float2 *in, float2 *out, const float2 *tw, int batch, float scale,
+                       cudaStream_t st) {
+#define CALL(L) launch_cfft_t<L>(inv, in, out, tw, batch, scale, st)
+  B2F_DISPATCH_LOGN(logn, CALL)
+#undef CALL
+}
+static int launch_rfft(int logn, bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *w2,
+                       int batch, cudaStream_t st) {
+#define CALL(L) launch_rfft_t<L>(inv, in, out, tw, w2, batch, st)
+  B2F_DISPATCH_LOGN(logn, CALL)
+#undef CALL
+}
+
+
+// ---- four-step plan for N > 2^kMaxSmemLogN ----------------------------------------------------------------
+struct LargePlan {
+  int logn = 0, log1 = 0, log2 = 0, chunk = 1;
+  float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twl = nullptr, *d_scratch = nullptr;
+  // transforms per chunk: the scratch matrix of a chunk should stay in the 126 MB L2 between the two steps
+  static constexpr size_t kScratchBytes = 32u << 20;
+  int init(int logn_, int max_batch) {
+    logn = logn_;
+    log1 = logn / 2;
+    log2 = logn - log1;
+    const int N = 1 << logn, N2 = 1 << log2, N1 = 1 << log1;
+    int rc;
+    if ((rc = upload(make_pass_twiddles(log1), &d_tw1))) return rc;
+    if ((rc = upload(make_pass_twiddles(log2), &d_tw2))) return rc;
+    std::vector<float2> twl((size_t)N);
+    for (int k1 = 0; k1 < N1; k1++)
+      for (int n2 = 0; n2 < N2; n2++) twl[(size_t)k1 * N2 + n2] = ref_twiddle((long long)n2 * k1, N);
+    if ((rc = upload(twl, &d_twl))) return rc;
+    chunk = (int)(kScratchBytes / ((size_t)N * sizeof(float2)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > max_batch) chunk = max_batch < 1 ? 1 : max_batch;
+    CK(cudaMalloc((void **)&d_scratch, (size_t)chunk * N * sizeof(float2)));
+    return B2F_OK;
+  }
+  void destroy() {
+    for (void *p : {(void *)d_tw1, (void *)d_tw2, (void *)d_twl, (void *)d_scratch})
+      if (p) cudaFree(p);
+    d_tw1 = d_tw2 = d_twl = d_scratch = nullptr;
+  }
+  template <int L1, int L2, bool INV>
+  int run_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st) {
+    using L = LargeGeom<L1, L2>;
+    int rc;
+    if ((rc = set_smem(large_cols_kernel<L1, L2, INV>, L::SMEM_A))) return rc;
+    if ((rc = set_smem(large_rows_kernel<L1, L2, INV>, L::SMEM_B))) return rc;
+    for (int b0 = 0; b0 < batch; b0 += chunk) {
+      const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+      const int gxa = L::N2 / L::C, gxb = L::N1 / L::RB;
+      int gya = (592 + gxa - 1) / gxa, gyb = (592 + gxb - 1) / gxb;
+      if (gya > nb) gya = nb;
+      if (gyb > nb) gyb = nb;
+      const float2 *src = in + (size_t)b0 * L::N;
+      float2 *dst = out + (size_t)b0 * L::N;
+      large_cols_kernel<L1, L2, INV><<<dim3(gxa, gya), L::THREADS, L::SMEM_A, st>>>(src, d_scratch, d_tw1, d_twl, nb);
+      CK(cudaGetLastError());
+      large_rows_kernel<L1, L2, INV><<<dim3(gxb, gyb), L::THREADS, L::SMEM_B, st>>>(d_scratch, dst, d_tw2, nb, scale);
+      CK(cudaGetLastError());
+    }
+    return B2F_OK;
+  }
+  int run_c2c(bool inv, const float2 *in, float2 *out, int batch, float scale, cudaStream_t st) {
+    if (logn == 15) return inv ? run_t<7, 8, true>(in, out, batch, scale, st) : run_t<7, 8, false>(in, out, batch, scale, st);
+    if (logn == 16) return inv ? run_t<8, 8, true>(in, out, batch, scale, st) : run_t<8, 8, false>(in, out, batch, scale, st);
+    return B2F_ERR_UNSUPPORTED;
+  }
+  int run_real(bool inv, const float2 *in, float2 *out, const float2 *w2, int batch, cudaStream_t st) {
+    const int N = 1 << logn;
+    const long long pairs = (long long)batch * (N / 2);
+    const int grid = (int)((pairs + 255) / 256);
+    int rc;
+    if (!inv) {
+      if ((rc = run_c2c(false, in, out, batch, 1.0f / (float)N, st))) return rc;
+      rfft_split_kernel<false><<<grid, 256, 0, st>>>(out, out, w2, N, pairs);
+      CK(cudaGetLastError());
+    } else {
+      rfft_split_kernel<true><<<grid, 256, 0, st>>>(in, out, w2, N, pairs);
+      CK(cudaGetLastError());
+      if ((rc = run_c2c(true, out, out, batch, 1.0f, st))) return rc;
+    }
+    return B2F_OK;
+  }
+};
+
+// ---- pinned staging helper -----------------------------------------------------------------------------
+// Host entry points move data through a pinned bounce buffer when it is small (latency path: one
+// block / one transform), and straight from the caller's memory when it is large (the DMA engine
+// handles pageable or caller-pinned memory itself).
+struct Staging {
+  void *pin = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return B2F_OK;
+    if (pin) cudaFreeHost(pin);
+    pin = nullptr;
+    cap = 0;
+    CK(cudaMallocHost(&pin, bytes));
+    cap = bytes;
+    return B2F_OK;
+  }
+  void release() {
+    if (pin) cudaFreeHost(pin);
+    pin = nullptr;
+    cap = 0;
+  }
+};
+static const size_t kBounceMax = 1u << 20;
+
+static int h2d(void *dst, const void *src, size_t bytes, Staging &sg, cudaStream_t st) {
+  if (bytes <= kBounceMax) {
+    int rc = sg.ensure(kBounceMax);
+    if (rc) return rc;
+    memcpy(sg.pin, src, bytes);
+    CK(cudaMemcpyAsync(dst, sg.pin, bytes, cudaMemcpyHostToDevice, st));
+  } else {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+  }
+  return B2F_OK;
+}
+// blocking: returns when dst holds the data
+static int d2h(void *dst, const void *src, size_t bytes, Staging &sg, cudaStream_t st) {
+  if (bytes <= kBounceMax) {
+    int rc = sg.ensure(kBounceMax);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(sg.pin, src, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(dst, sg.pin, bytes);
+  } else {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return B2F_OK;
+}
+
+// =====================================================================================================
+// complex / real FFT plans
+// =====================================================================================================
+struct FftPlanCore {
+  int device = 0, N = 0, logn = 0, fwd = 1, max_batch = 1;
+  float2 *d_tw = nullptr;   // pass twiddles (small path) or sub-plan twiddles (large path)
+  float2 *d_w2 = nullptr;   // split twiddles (real plans)
+  float2 *d_buf = nullptr;  // device buffer backing the host entry points
+  LargePlan large;          // N > 2^kMaxSmemLogN
+  cudaStream_t stream = nullptr;
+  Staging sg_in, sg_out;
+  bool is_large() const { return logn > kMaxSmemLogN; }
+  int init(int dev, int n, int f, int mb, bool real) {
+    device = dev, N = n, fwd = f ? 1 : 0, max_batch = mb < 1 ? 1 : mb;
+    logn = ilog2_exact(n);
+    int rc = check_device(dev);
+    if (rc) return rc;
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (is_large()) {
+      rc = large.init(logn, max_batch);
+      if (rc) return rc;
+    } else {
+      rc = upload(make_pass_twiddles(logn), &d_tw);
+      if (rc) return rc;
+    }
+    if (real) {
+      rc = upload(make_split_twiddles(N), &d_w2);
+      if (rc) return rc;
+    }
+    return B2F_OK;
+  }
+  int ensure_buf() {
+    if (!d_buf) CK(cudaMalloc((void **)&d_buf, (size_t)max_batch * N * sizeof(float2)));
+    return B2F_OK;
+  }
+  void destroy() {
+    cudaSetDevice(device);
+    if (d_tw) cudaFree(d_tw);
+    if (d_w2) cudaFree(d_w2);
+    if (d_buf) cudaFree(d_buf);
+    large.destroy();
+    if (stream) cudaStreamDestroy(stream);
+    sg_in.release();
+    sg_out.release();
+  }
+  int run_c2c(const float2 *in, float2 *out, int batch, cudaStream_t st) {
+    const float scale = fwd ? 1.0f / (float)N : 1.0f;
+    if (is_large()) return large.run_c2c(!fwd, in, out, batch, scale, st);
+    return launch_cfft(logn, !fwd, in, out, d_tw, batch, scale, st);
+  }
+  int run_real(const float2 *in, float2 *out, int batch, cudaStream_t st) {
+    if (is_large()) return large.run_real(!fwd, in, out, d_w2, batch, st);
+    return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, batch, st);
+  }
+};
+
+struct b2f_cfft {
+  FftPlanCore core;
+};
+struct b2f_rfft {
+  FftPlanCore core;
+};
+
+extern "C" int b2f_cfft_create(b2f_cfft **plan, int device, int N, int fwd, int max_batch) {
+  if (!plan) return B2F_ERR_INVALID_VALUE;
+  *plan = nullptr;
+  const int logn = ilog2_exact(N);
+  if (logn < 1) return B2F_ERR_INVALID_VALUE;
+  if (logn > kMaxLogN) return B2F_ERR_UNSUPPORTED;
+  b2f_cfft *p = new (std::nothrow) b2f_cfft;
+  if (!p) return B2F_ERR_ALLOC;
+  int rc = p->core.init(device, N, fwd, max_batch, false);
+  if (rc) {
+    p->core.destroy();
+    delete p;
+    return rc;
+  }
+  *plan = p;
+  return B2F_OK;
+}
+extern "C" int b2f_cfft_destroy(b2f_cfft *plan) {
+  if (!plan) return B2F_OK;
+  plan->core.destroy();
+  delete plan;
+  return B2F_OK;
+}
+extern "C" int b2f_cfft_exec_dev(b2f_cfft *plan, const void *d_in, void *d_out, int batch, void *stream) {
+  if (!plan || !d_in || !d_out || batch < 0) return B2F_ERR_INVALID_VALUE;
+  if (batch == 0) return B2F_OK;
+  FftPlanCore &c = plan->core;
+  CK(cudaSetDevice(c.device));
+  return c.run_c2c((const float2 *)d_in, (float2 *)d_out, batch, (cudaStream_t)stream);
+}
+extern "C" int b2f_cfft_exec_host(b2f_cfft *plan, float *cdata, int batch) {
+  if (!plan || !cdata || batch < 0) return B2F_ERR_INVALID_VALUE;
+  if (batch == 0) return B2F_OK;
+  FftPlanCore &c = plan->core;
+  if (batch > c.max_batch) return B2F_ERR_BATCH;
+  CK(cudaSetDevice(c.device));
+  int rc = c.ensure_buf();
+  if (rc) return rc;
+  const size_t bytes = (size_t)batch * c.N * sizeof(float2);
+  if ((rc = h2d(c.d_buf, cdata, bytes, c.sg_in, c.stream))) return rc;
+  if ((rc = c.run_c2c(c.d_buf, c.d_buf, batch, c.stream))) return rc;
+  return d2h(cdata, c.d_buf, bytes, c.sg_out, c.stream);
+}
+
+extern "C" int b2f_rfft_create(b2f_rfft **plan, int device, int size, int fwd, int max_batch) {
+  if (!plan) return B2F_ERR_INVALID_VALUE;
+  *plan = nullptr;
+  const int logs = ilog2_exact(size);
+  if (logs < 2) return B2F_ERR_INVALID_VALUE;
+  if (logs - 1 > kMaxLogN) return B2F_ERR_UNSUPPORTED;
+  b2f_rfft *p = new (std::nothrow) b2f_rfft;
+  if (!p) return B2F_ERR_ALLOC;
+  int rc = p->core.init(device, size / 2, fwd, max_batch, true);
+  if (rc) {
+    p->core.destroy();
+    delete p;
+    return rc;
+  }
+  *plan = p;
+  return B2F_OK;
+}
+extern "C" int b2f_rfft_destroy(b2f_rfft *plan) {
+  if (!plan) return B2F_OK;
+  plan->core.destroy();
+  delete plan;
+  return B2F_OK;
+}
+extern "C" int b2f_rfft_exec_dev(b2f_rfft *plan, const void *d_in, void *d_out, int batch, void *stream) {
+  if (!plan || !d_in || !d_out || batch < 0) return B2F_ERR_INVALID_VALUE;
+  if (batch == 0) return B2F_OK;
+  FftPlanCore &c = plan->core;
+  CK(cudaSetDevice(c.device));
+  return c.run_real((const float2 *)d_in, (float2 *)d_out, batch, (cudaStream_t)stream);
+}
+extern "C" int b2f_rfft_exec_host(b2f_rfft *plan, float *cdata, float *r, int batch) {
+  if (!plan || !cdata || !r || batch < 0) return B2F_ERR_INVALID_VALUE;
+  if (batch == 0) return B2F_OK;
+  FftPlanCore &c = plan->core;
+  if (batch > c.max_batch) return B2F_ERR_BATCH;
+  CK(cudaSetDevice(c.device));
+  int rc = c.ensure_buf();
+  if (rc) return rc;
+  const size_t bytes = (size_t)batch * c.N * sizeof(float2);
+  // forward reads the reals (cl_fft.cpp:273-275), inverse reads the spectrum (284)
+  const void *src = c.fwd ? (const void *)r : (const void *)cdata;
+  if ((rc = h2d(c.d_buf, src, bytes, c.sg_in, c.stream))) return rc;
+  if ((rc = c.run_real(c.d_buf, c.d_buf, batch, c.stream))) return rc;
+  if ((rc = d2h(cdata, c.d_buf, bytes, c.sg_out, c.stream))) return rc;       // 281 / 290
+  if (!c.fwd && (void *)r != (void *)cdata) memcpy(r, cdata, bytes);          // 292-293
+  return B2F_OK;
+}
+
+// =====================================================================================================
+// partitioned convolution
+// =====================================================================================================
+struct b2f_pconv {
+  int device = 0, cvs = 0, pts = 0, logp = 0, nparts = 0, channels = 1;
+  int wp = 0, wp2 = 0;  // ring positions, cl_conv.cpp:144
+  float2 *d_fdl = nullptr, *d_irs = nullptr, *d_tw = nullptr, *d_w2 = nullptr;
+  float *d_tail = nullptr, *d_in1 = nullptr, *d_in2 = nullptr, *d_out = nullptr, *d_ir = nullptr;
+  cudaStream_t stream = nullptr;
+  Staging sg_in, sg_in2, sg_out;
+  int cluster = 1;
+  size_t ring_elems() const { return (size_t)channels * nparts * pts; }
+  void destroy() {
+    cudaSetDevice(device);
+    for (void *p : {(void *)d_fdl, (void *)d_irs, (void *)d_tw, (void *)d_w2, (void *)d_tail, (void *)d_in1,
+                    (void *)d_in2, (void *)d_out, (void *)d_ir})
+      if (p) cudaFree(p);
+    if (stream) cudaStreamDestroy(stream);
+    sg_in.release();
+    sg_in2.release();
+    sg_out.release();
+  }
+};
+
+template <int LOGP>
+static int pconv_smem_bytes(bool tv) {
+  using P = PconvGeom<LOGP>;
+  const int fft = P::FFT_SMEM + (P::FFT_SMEM & 1);
+  const int partial4 = (P::TILES > 1 ? 2 : 1) * P::HALF;
+  return (tv ? 2 : 1) * fft * (int)sizeof(float2) + partial4 * (int)sizeof(float4);
+}
+
+template <int LOGP, bool TV>
+static int launch_pconv_step_t(const PconvArgs &a, int channels, int S, cudaStream_t st) {
+  using P = PconvGeom<LOGP>;
+  const int smem = pconv_smem_bytes<LOGP>(TV);
+  int rc = set_smem(pconv_step_kernel<LOGP, TV>, smem);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(S, channels, 1);
+  cfg.blockDim = dim3(P::NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, pconv_step_kernel<LOGP, TV>, a));
+  return B2F_OK;
+}
+template <int LOGP>
+static int launch_pconv_push_t(const float *ir, size_t stride, b2f_pconv *h, cudaStream_t st) {
+  using P = PconvGeom<LOGP>;
+  const int smem = (P::FFT_SMEM + 1) * (int)sizeof(float2);
+  int rc = set_smem(pconv_push_ir_kernel<LOGP>, smem);
+  if (rc) return rc;
+  dim3 grid(h->nparts, h->channels, 1);
+  pconv_push_ir_kernel<LOGP><<<grid, P::NTHREADS, smem, st>>>(ir, stride, h->d_irs, h->d_tw, h->d_w2, h->nparts, h->wp2);
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
+
+#define B2F_DISPATCH_LOGP(logp, CALL)    \
+  switch (logp) {                        \
+    case 1: return CALL(1);              \
+    case 2: return CALL(2);              \
+    case 3: return CALL(3);              \
+    case 4: return CALL(4);              \
+    case 5: return CALL(5);              \
+    case 6: return CALL(6);              \
+    case 7: return CALL(7);              \
+    case 8: return CALL(8);              \
+    case 9: return CALL(9);              \
+    case 10: return CALL(10);            \
+    case 11: return CALL(11);            \
+    case 12: return CALL(12);            \
+    default: return B2F_ERR_UNSUPPORTED; \
+  }
+
+static int launch_pconv_step(int logp, bool tv, const PconvArgs &a, int channels, int S, cudaStream_t st) {
+  if (tv) {
+#define CALL(L) launch_pconv_step_t<L, true>(a, channels, S, st)
+    B2F_DISPATCH_LOGP(logp, CALL)
+#undef CALL
+  } else {
+#define CALL(L) launch_pconv_step_t<L, false>(a, channels, S, st)
+    B2F_DISPATCH_LOGP(logp, CALL)
+#undef CALL
+  }
+}
+static int launch_pconv_push(int logp, const float *ir, size_t stride, b2f_pconv *h, cudaStream_t st) {
+#define CALL(L) launch_pconv_push_t<L>(ir, stride, h, st)
+  B2F_DISPATCH_LOGP(logp, CALL)
+#undef CALL
+}
+
+extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, int channels) {
+  if (!out) return B2F_ERR_INVALID_VALUE;
+  *out = nullptr;
+  const int logp = ilog2_exact(pts);
+  if (logp < 1 || cvs < pts || channels < 1) return B2F_ERR_INVALID_VALUE;
+  if (logp > kPconvMaxLogP || channels > 65535) return B2F_ERR_UNSUPPORTED;
+  int rc = check_device(device);
+  if (rc) return rc;
+  b2f_pconv *h = new (std::nothrow) b2f_pconv;
+  if (!h) return B2F_ERR_ALLOC;
+  h->device = device, h->cvs = cvs, h->pts = pts, h->logp = logp, h->channels = channels;
+  h->nparts = cvs / pts;  // truncating, cl_conv.cpp:143
+  h->wp = 0;
+  h->wp2 = h->nparts - 1;
+  // enough CTAs to cover the 148 SMs twice when there are few channels: split the partitions over a
+  // thread-block cluster (portable size limit 8)
+  int S = 1;
+  while (S < 8 && channels * S < 296 && S * 2 <= h->nparts) S *= 2;
+  h->cluster = S;
+  auto fail = [&](int code) {
+    h->destroy();
+    delete h;
+    return code;
+  };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "stream"));
+  if ((rc = upload(make_pass_twiddles(logp), &h->d_tw))) return fail(rc);
+  if ((rc = upload(make_split_twiddles(pts), &h->d_w2))) return fail(rc);
+  const size_t ring = h->ring_elems() * sizeof(float2), blk = (size_t)channels * pts * sizeof(float);
+  if ((e = cudaMalloc((void **)&h->d_fdl, ring)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc fdl"));
+  if ((e = cudaMalloc((void **)&h->d_irs, ring)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc irs"));
+  if ((e = cudaMalloc((void **)&h->d_tail, blk)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc tail"));
+  // zero state, cl_conv.cpp:303-313
+  if ((e = cudaMemsetAsync(h->d_fdl, 0, ring, h->stream)) != cudaSuccess) return fail(cuda_fail(e, "memset"));
+  if ((e = cudaMemsetAsync(h->d_irs, 0, ring, h->stream)) != cudaSuccess) return fail(cuda_fail(e, "memset"));
+  if ((e = cudaMemsetAsync(h->d_tail, 0, blk, h->stream)) != cudaSuccess) return fail(cuda_fail(e, "memset"));
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(cuda_fail(e, "sync"));
+  *out = h;
+  return B2F_OK;
+}
+extern "C" int b2f_pconv_destroy(b2f_pconv *h) {
+  if (!h) return B2F_OK;
+  h->destroy();
+  delete h;
+  return B2F_OK;
+}
+extern "C" int b2f_pconv_nparts(const b2f_pconv *h) { return h ? h->nparts : 0; }
+
+extern "C" int b2f_pconv_reset(b2f_pconv *h) {
+  if (!h) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->d_fdl, 0, h->ring_elems() * sizeof(float2), h->stream));
+  CK(cudaMemsetAsync(h->d_tail, 0, (size_t)h->channels * h->pts * sizeof(float), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->wp = 0;
+  h->wp2 = h->nparts - 1;
+  return B2F_OK;
+}
+
+extern "C" int b2f_pconv_push_ir_dev(b2f_pconv *h, const void *d_ir, size_t ir_stride, void *stream) {
+  if (!h || !d_ir || ir_stride < (size_t)h->nparts * h->pts) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  int rc = launch_pconv_push(h->logp, (const float *)d_ir, ir_stride, h, (cudaStream_t)stream);
+  // after nparts decrements the write position is back where it started (cl_conv.cpp:385)
+  return rc;
+}
+extern "C" int b2f_pconv_push_ir_host(b2f_pconv *h, const float *ir, size_t ir_stride) {
+  if (!h || !ir || ir_stride < (size_t)h->nparts * h->pts) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  const size_t per = (size_t)h->nparts * h->pts;
+  if (!h->d_ir) CK(cudaMalloc((void **)&h->d_ir, (size_t)h->channels * per * sizeof(float)));
+  CK(cudaMemcpy2DAsync(h->d_ir, per * sizeof(float), ir, ir_stride * sizeof(float), per * sizeof(float), h->channels,
+                       cudaMemcpyHostToDevice, h->stream));
+  int rc = launch_pconv_push(h->logp, h->d_ir, per, h, h->stream);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return B2F_OK;
+}
+
+static int pconv_enqueue(b2f_pconv *h, bool tv, float *d_out, const float *d_in1, const float *d_in2, cudaStream_t st) {
+  PconvArgs a;
+  a.fdl = h->d_fdl, a.irs = h->d_irs, a.tail = h->d_tail;
+  a.in1 = d_in1, a.in2 = d_in2, a.out = d_out;
+  a.tw = h->d_tw, a.w2 = h->d_w2;
+  a.nparts = h->nparts, a.wp = h->wp, a.wp2 = h->wp2;
+  int rc = launch_pconv_step(h->logp, tv, a, h->channels, h->cluster, st);
+  if (rc) return rc;
+  h->wp = h->wp != h->nparts - 1 ? h->wp + 1 : 0;             // cl_conv.cpp:424
+  if (tv) h->wp2 = h->wp2 == 0 ? h->nparts - 1 : h->wp2 - 1;  // cl_conv.cpp:519
+  return B2F_OK;
+}
+extern "C" int b2f_pconv_process_dev(b2f_pconv *h, void *d_out, const void *d_in, void *stream) {
+  if (!h || !d_out || !d_in) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  return pconv_enqueue(h, false, (float *)d_out, (const float *)d_in, nullptr, (cudaStream_t)stream);
+}
+extern "C" int b2f_pconv_process_tv_dev(b2f_pconv *h, void *d_out, const void *d_in1, const void *d_in2, void *stream) {
+  if (!h || !d_out || !d_in1 || !d_in2) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  return pconv_enqueue(h, true, (float *)d_out, (const float *)d_in1, (const float *)d_in2, (cudaStream_t)stream);
+}
+static int pconv_host_bufs(b2f_pconv *h, bool tv) {
+  const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
+  if (!h->d_in1) CK(cudaMalloc((void **)&h->d_in1, blk));
+  if (!h->d_out) CK(cudaMalloc((void **)&h->d_out, blk));
+  if (tv && !h->d_in2) CK(cudaMalloc((void **)&h->d_in2, blk));
+  return B2F_OK;
+}
+extern "C" int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in) {
+  if (!h || !out || !in) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  int rc = pconv_host_bufs(h, false);
+  if (rc) return rc;
+  const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
+  if ((rc = h2d(h->d_in1, in, blk, h->sg_in, h->stream))) return rc;
+  if ((rc = pconv_enqueue(h, false, h->d_out, h->d_in1, nullptr, h->stream))) return rc;
+  return d2h(out, h->d_out, blk, h->sg_out, h->stream);
+}
+extern "C" int b2f_pconv_process_tv_host(b2f_pconv *h, float *out, const float *in1, const float *in2) {
+  if (!h || !out || !in1 || !in2) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  int rc = pconv_host_bufs(h, true);
+  if (rc) return rc;
+  const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
+  if ((rc = h2d(h->d_in1, in1, blk, h->sg_in, h->stream))) return rc;
+  if ((rc = h2d(h->d_in2, in2, blk, h->sg_in2, h->stream))) return rc;
+  if ((rc = pconv_enqueue(h, true, h->d_out, h->d_in1, h->d_in2, h->stream))) return rc;
+  return d2h(out, h->d_out, blk, h->sg_out, h->stream);
+}
+extern "C" int b2f_pconv_read_spectra(b2f_pconv *h, int which, int channel, float *dst) {
+  if (!h || !dst || channel < 0 || channel >= h->channels || (which != 1 && which != 2)) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  const size_t per = (size_t)h->nparts * h->pts;
+  const float2 *src = (which == 1 ? h->d_fdl : h->d_irs) + (size_t)channel * per;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(dst, src, per * sizeof(float2), cudaMemcpyDeviceToHost));
+  return B2F_OK;
+}
+
+// =====================================================================================================
+// direct convolution
+// =====================================================================================================
+struct b2f_dconv {
+  int device = 0, irsize = 0, vsize = 0, channels = 1, max_blocks = 1;
+  int wp = 0;  // the reference's ring position (cl_dconv.cpp:124), kept for the coefficient ring
+  int cur = 0; // which history buffer is current
+  float *d_hist[2] = {nullptr, nullptr};
+  float *d_coefs = nullptr, *d_in1 = nullptr, *d_in2 = nullptr, *d_out = nullptr;
+  cudaStream_t stream = nullptr;
+  Staging sg_in, sg_in2, sg_out;
+  int L() const { return irsize + vsize; }
+  void destroy() {
+    cudaSetDevice(device);
+    for (void *p : {(void *)d_hist[0], (void *)d_hist[1], (void *)d_coefs, (void *)d_in1, (void *)d_in2, (void *)d_out})
+      if (p) cudaFree(p);
+    if (stream) cudaStreamDestroy(stream);
+    sg_in.release();
+    sg_in2.release();
+    sg_out.release();
+  }
+};
+
+extern "C" int b2f_dconv_create(b2f_dconv **out, int device, int irsize, int vsize, int channels, int max_blocks) {
+  if (!out) return B2F_ERR_INVALID_VALUE;
+  *out = nullptr;
+  if (irsize < 1 || vsize < 1 || channels < 1) return B2F_ERR_INVALID_VALUE;
+  if (channels > 65535) return B2F_ERR_UNSUPPORTED;
+  int rc = check_device(device);
+  if (rc) return rc;
+  b2f_dconv *h = new (std::nothrow) b2f_dconv;
+  if (!h) return B2F_ERR_ALLOC;
+  h->device = device, h->irsize = irsize, h->vsize = vsize, h->channels = channels;
+  h->max_blocks = max_blocks < 1 ? 1 : max_blocks;
+  auto fail = [&](int code) {
+    h->destroy();
+    delete h;
+    return code;
+  };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "stream"));
+  const size_t hb = (size_t)channels * irsize * sizeof(float), cb = (size_t)channels * h->L() * sizeof(float);
+  for (int i = 0; i < 2; i++) {
+    if ((e = cudaMalloc((void **)&h->d_hist[i], hb)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc hist"));
+    if ((e = cudaMemsetAsync(h->d_hist[i], 0, hb, h->stream)) != cudaSuccess) return fail(cuda_fail(e, "memset"));
+  }
+  if ((e = cudaMalloc((void **)&h->d_coefs, cb)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc coefs"));
+  if ((e = cudaMemsetAsync(h->d_coefs, 0, cb, h->stream)) != cudaSuccess) return fail(cuda_fail(e, "memset"));
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(cuda_fail(e, "sync"));
+  *out = h;
+  return B2F_OK;
+}
+extern "C" int b2f_dconv_destroy(b2f_dconv *h) {
+  if (!h) return B2F_OK;
+  h->destroy();
+  delete h;
+  return B2F_OK;
+}
+extern "C" int b2f_dconv_reset(b2f_dconv *h) {
+  if (!h) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  for (int i = 0; i < 2; i++) CK(cudaMemsetAsync(h->d_hist[i], 0, (size_t)h->channels * h->irsize * sizeof(float), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->wp = 0;
+  return B2F_OK;
+}
+extern "C" int b2f_dconv_push_ir_dev(b2f_dconv *h, const void *d_ir, size_t ir_stride, void *stream) {
+  if (!h || !d_ir || ir_stride < (size_t)h->irsize) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy2DAsync(h->d_coefs, (size_t)h->L() * sizeof(float), d_ir, ir_stride * sizeof(float),
+                       (size_t)h->irsize * sizeof(float), h->channels, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return B2F_OK;
+}
+extern "C" int b2f_dconv_push_ir_host(b2f_dconv *h, const float *ir, size_t ir_stride) {
+  if (!h || !ir || ir_stride < (size_t)h->irsize) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy2DAsync(h->d_coefs, (size_t)h->L() * sizeof(float), ir, ir_stride * sizeof(float),
+                       (size_t)h->irsize * sizeof(float), h->channels, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B2F_OK;
+}
+
+static bool tiles_too_many(long long nout) { return (nout + kDcTileOut - 1) / kDcTileOut > 65535; }
+static int dconv_enqueue(b2f_dconv *h, float *d_out, const float *d_in, int nblocks, cudaStream_t st) {
+  DconvArgs a;
+  a.hist_in = h->d_hist[h->cur];
+  a.hist_out = h->d_hist[h->cur ^ 1];
+  a.coefs = h->d_coefs;
+  a.in = d_in, a.out = d_out;
+  a.irsize = h->irsize, a.vsize = h->vsize, a.nout = nblocks * h->vsize;
+  a.coef_stride = h->L();
+  const int tiles = (a.nout + kDcTileOut - 1) / kDcTileOut;
+  // split the taps over a cluster when the grid would not cover the GPU
+  int S = 1;
+  while (S < 8 && (long long)tiles * h->channels * S < 296 && h->irsize / (S * 2) >= 64) S *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(S, tiles, h->channels);
+  cfg.blockDim = dim3(kDcThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, dconv_fir_kernel, a));
+  h->cur ^= 1;
+  h->wp = (int)(((long long)h->wp + (long long)nblocks * h->vsize) % h->L());  // cl_dconv.cpp:124
+  return B2F_OK;
+}
+extern "C" int b2f_dconv_process_dev(b2f_dconv *h, void *d_out, const void *d_in, int nblocks, void *stream) {
+  if (!h || !d_out || !d_in || nblocks < 1) return B2F_ERR_INVALID_VALUE;
+  if (tiles_too_many((long long)nblocks * h->vsize)) return B2F_ERR_UNSUPPORTED;
+  CK(cudaSetDevice(h->device));
+  return dconv_enqueue(h, (float *)d_out, (const float *)d_in, nblocks, (cudaStream_t)stream);
+}
+static int dconv_coef_write(b2f_dconv *h, const float *d_in2, cudaStream_t st) {
+  dim3 grid((h->vsize + 255) / 256, h->channels, 1);
+  dconv_coef_write_kernel<<<grid, 256, 0, st>>>(h->d_coefs, d_in2, h->vsize, h->L(), h->wp);
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
+extern "C" int b2f_dconv_process_tv_dev(b2f_dconv *h, void *d_out, const void *d_in1, const void *d_in2, void *stream) {
+  if (!h || !d_out || !d_in1 || !d_in2) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  int rc = dconv_coef_write(h, (const float *)d_in2, (cudaStream_t)stream);
+  if (rc) return rc;
+  return dconv_enqueue(h, (float *)d_out, (const float *)d_in1, 1, (cudaStream_t)stream);
+}
+static int dconv_host_bufs(b2f_dconv *h, bool tv) {
+  const size_t blk = (size_t)h->channels * h->max_blocks * h->vsize * sizeof(float);
+  if (!h->d_in1) CK(cudaMalloc((void **)&h->d_in1, blk));
+  if (!h->d_out) CK(cudaMalloc((void **)&h->d_out, blk));
+  if (tv && !h->d_in2) CK(cudaMalloc((void **)&h->d_in2, (size_t)h->channels * h->vsize * sizeof(float)));
+  return B2F_OK;
+}
+extern "C" int b2f_dconv_process_host(b2f_dconv *h, float *out, const float *in, int nblocks) {
+  if (!h || !out || !in || nblocks < 1) return B2F_ERR_INVALID_VALUE;
+  if (nblocks > h->max_blocks) return B2F_ERR_BATCH;
+  CK(cudaSetDevice(h->device));
+  int rc = dconv_host_bufs(h, false);
+  if (rc) return rc;
+  const size_t bytes = (size_t)h->channels * nblocks * h->vsize * sizeof(float);
+  if ((rc = h2d(h->d_in1, in, bytes, h->sg_in, h->stream))) return rc;
+  if ((rc = dconv_enqueue(h, h->d_out, h->d_in1, nblocks, h->stream))) return rc;
+  return d2h(out, h->d_out, bytes, h->sg_out, h->stream);
+}
+extern "C" int b2f_dconv_process_tv_host(b2f_dconv *h, float *out, const float *in1, const float *in2) {
+  if (!h || !out || !in1 || !in2) return B2F_ERR_INVALID_VALUE;
+  CK(cudaSetDevice(h->device));
+  int rc = dconv_host_bufs(h, true);
+  if (rc) return rc;
+  const size_t bytes = (size_t)h->channels * h->vsize * sizeof(float);
+  if ((rc = h2d(h->d_in1, in1, bytes, h->sg_in, h->stream))) return rc;
+  if ((rc = h2d(h->d_in2, in2, bytes, h->sg_in2, h->stream))) return rc;
+  if ((rc = dconv_coef_write(h, h->d_in2, h->stream))) return rc;
+  if ((rc = dconv_enqueue(h, h->d_out, h->d_in1, 1, h->stream))) return rc;
+  return d2h(out, h->d_out, bytes, h->sg_out, h->stream);
+}

@@ -1,0 +1,325 @@
+// pconv_kernels.cuh -- uniformly-partitioned convolution, one fused launch per streaming block.
+//
+// Replaces cl_conv::Clpconv's 24 launches + 2 copies per block (cl_conv.cpp:393-458; kernels
+// cl_conv_kernels.h:46-124): reorder, 9x fft, r2c, convol (bsize work-items x 2 CAS atomics),
+// c2r, reorder, 9x fft, olap. Here, per channel, one CTA (or one thread-block cluster that splits
+// the partitions and reduces through distributed shared memory) does
+//   forward real FFT of the new block -> frequency-domain delay line (FDL) frame `wp`
+//   Y[n] = sum_p FDL[(wp+1+p) mod nparts][n] * IR[p][n]   streamed with 128-bit loads, accumulated in
+//          registers in ascending p (deterministic; the reference's atomic order is unspecified, Q8)
+//   unsplit -> inverse FFT -> /pts -> overlap-add with the saved tail -> out, new tail
+// Algorithmic HBM traffic per channel-block: 8*pts*(2*nparts+3) bytes; the MAC loop moves
+// all but 3/(2*nparts+3) of it.
+//
+// Data layout in HBM (channel-major, everything contiguous per channel):
+//   fdl  [channels][nparts][pts] float2   the reference's spec1 ring, same frame order
+//   irs  [channels][nparts][pts] float2   the reference's spec2 ring, same frame order
+//   tail [channels][pts]         float    saved second half of the last inverse FFT, unnormalised
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "fft_core.cuh"
+
+namespace b2f {
+
+namespace cg = cooperative_groups;
+
+constexpr int kPconvMaxLogP = 12;  // fused path: pts <= 4096 (shared-memory budget incl. time-varying)
+
+template <int LOGP>
+struct PconvGeom {
+  using G = FftGeom<LOGP>;
+  static constexpr int PTS = 1 << LOGP;
+  static constexpr int T = G::T;                           // threads carrying the real transform
+  static constexpr int FT = T < 32 ? 32 : T;               // FFT participants (whole warps)
+  static constexpr int VT = FT / T;                        // virtual transforms (only #0 is real)
+  static constexpr int HALF = PTS / 2 < 1 ? 1 : PTS / 2;   // float4 per frame
+  static constexpr int THREADS = HALF < 32 ? 32 : (HALF > 256 ? 256 : HALF);
+  static constexpr int NTHREADS = THREADS > FT ? THREADS : FT;
+  static constexpr int TILES = (HALF + NTHREADS - 1) / NTHREADS;
+  static constexpr int FFT_SMEM = VT * G::SMEM;            // float2 entries per FFT work buffer
+};
+
+// barrier over the FFT participants only (warps 0 .. FT/32-1); id 1, the CTA barrier is id 0
+template <int COUNT>
+struct FftGroupSync {
+  __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, %0;" ::"n"(COUNT) : "memory"); }
+};
+
+// R(x): zero-pad pts reals to 2*pts, pack as pts complex, unscaled forward FFT, real-FFT split.
+// (cl_conv.cpp:399-419 / 361-380; kernels cl_conv_kernels.h:46-85.) Result left in sm (padded index).
+// Called by ALL threads of the CTA; x may be nullptr for CTAs that only need the barriers.
+template <int LOGP>
+__device__ __forceinline__ void pconv_forward_frame(const float *x, float2 *sm, const float2 *__restrict__ tw,
+                                                    const float2 *__restrict__ w2) {
+  using P = PconvGeom<LOGP>;
+  constexpr int N = P::PTS;
+  const int tid = threadIdx.x;
+  if (tid < P::FT) {
+    const int vt = tid / P::T, t = tid % P::T;
+    float2 *my = sm + vt * FftGeom<LOGP>::SMEM;
+    const bool real = (vt == 0);
+    auto load = [&](int idx, int) {
+      if (real && idx < N / 2) return *reinterpret_cast<const float2 *>(x + 2 * idx);
+      return make_float2(0.f, 0.f);
+    };
+    auto store = [&](int idx, float2 v, int) { my[pad_idx(idx)] = v; };
+    fft_run<LOGP, false, true>(load, store, my, tw, t, FftGroupSync<P::FT>());
+  }
+  __syncthreads();
+  for (int i = tid; i < N / 2; i += P::NTHREADS) {
+    if (i == 0) {
+      sm[pad_idx(0)] = rfft_dc<false>(sm[pad_idx(0)]);
+    } else {
+      float2 ci = sm[pad_idx(i)], cj = sm[pad_idx(N - i)];
+      rfft_pair<false>(ci, cj, __ldg(&w2[i]));
+      sm[pad_idx(i)] = ci;
+      sm[pad_idx(N - i)] = cj;
+    }
+  }
+  __syncthreads();
+}
+// pts == 2 corner: N/2 == 1, the pair loop above is empty except i == 0; element 1 (= N/2) untouched. OK.
+
+__device__ __forceinline__ void cmac2(float4 &acc, const float4 a, const float4 b) {
+  acc.x += a.x * b.x - a.y * b.y;
+  acc.y += a.x * b.y + a.y * b.x;
+  acc.z += a.z * b.z - a.w * b.w;
+  acc.w += a.z * b.w + a.w * b.z;
+}
+
+// acc += sum_{p < count} f[p] (*) g[p]; f/g advance one frame (stride4 float4) per p.
+// acc0 accumulates the reference's packed-bin product (re*re, im*im) (cl_conv_kernels.h:114-115) for
+// the first of the two bins; only the thread owning bin 0 uses it.
+template <int U>
+__device__ __forceinline__ void mac_segment(float4 &acc, float2 &acc0, const float4 *f, const float4 *g, int count,
+                                            size_t stride4) {
+  int p = 0;
+  for (; p + U <= count; p += U) {
+    float4 a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      a[u] = __ldcs(f + (size_t)(p + u) * stride4);
+      b[u] = __ldcs(g + (size_t)(p + u) * stride4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      cmac2(acc, a[u], b[u]);
+      acc0.x += a[u].x * b[u].x;
+      acc0.y += a[u].y * b[u].y;
+    }
+  }
+  for (; p < count; p++) {
+    float4 a = __ldcs(f + (size_t)p * stride4), b = __ldcs(g + (size_t)p * stride4);
+    cmac2(acc, a, b);
+    acc0.x += a.x * b.x;
+    acc0.y += a.y * b.y;
+  }
+}
+
+struct PconvArgs {
+  float2 *fdl;         // [channels][nparts][pts]
+  float2 *irs;         // [channels][nparts][pts]
+  float *tail;         // [channels][pts]
+  const float *in1;    // [channels][pts]
+  const float *in2;    // [channels][pts] (time-varying only)
+  float *out;          // [channels][pts]
+  const float2 *tw;    // pass twiddles of the pts-point plan
+  const float2 *w2;    // split twiddles exp(-i pi k / pts)
+  int nparts;
+  int wp;              // FDL write frame for this block (before the increment, cl_conv.cpp:406)
+  int wp2;             // IR write frame for this block (time-varying, cl_conv.cpp:487)
+};
+
+// grid = (S, channels), cluster = (S,1,1). Rank r of a cluster handles partitions
+// [r*nparts/S, (r+1)*nparts/S) minus the frames written in this very launch, which rank 0 takes
+// from its shared memory instead.
+template <int LOGP, bool TV>
+__global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS) pconv_step_kernel(PconvArgs a) {
+  using P = PconvGeom<LOGP>;
+  constexpr int PTS = P::PTS, HALF = P::HALF, NT = P::NTHREADS;
+  extern __shared__ float4 smem4[];
+  float2 *sX = reinterpret_cast<float2 *>(smem4);         // new input spectrum, later Y / IFFT buffer
+  float2 *sG = sX + P::FFT_SMEM + (P::FFT_SMEM & 1);      // new IR spectrum (TV only)
+  float4 *sP = reinterpret_cast<float4 *>(sG + (TV ? P::FFT_SMEM + (P::FFT_SMEM & 1) : 0));  // partials [HALF]
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int ch = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int nparts = a.nparts;
+  const size_t chan_off = (size_t)ch * nparts * PTS;
+  float2 *fdl = a.fdl + chan_off;
+  float2 *irs = a.irs + chan_off;
+
+  // ---- 1. forward transforms of the new block(s): rank 0 only -------------------------------------
+  if (rank == 0) {
+    pconv_forward_frame<LOGP>(a.in1 + (size_t)ch * PTS, sX, a.tw, a.w2);
+    if (TV) pconv_forward_frame<LOGP>(a.in2 + (size_t)ch * PTS, sG, a.tw, a.w2);
+    // store the new frames for future blocks (this launch never reads them back from HBM)
+    float2 *fx = fdl + (size_t)a.wp * PTS;
+    for (int i = tid; i < PTS; i += NT) fx[i] = sX[pad_idx(i)];
+    if (TV) {
+      float2 *gx = irs + (size_t)a.wp2 * PTS;
+      for (int i = tid; i < PTS; i += NT) gx[i] = sG[pad_idx(i)];
+    }
+  }
+
+  // ---- 2. spectral multiply-accumulate over this rank's partitions --------------------------------
+  // After the reference's increment (cl_conv.cpp:424) the read base is rp = wp+1 (mod nparts): the
+  // oldest frame. Partition p pairs FDL frame (rp+p) mod nparts with IR frame p; p = nparts-1 is the
+  // frame just written. In TV mode IR frame wp2 is also new.
+  const int rp = (a.wp + 1 == nparts) ? 0 : a.wp + 1;
+  const int p_lo = (int)((long long)rank * nparts / S);
+  const int p_hi = (int)((long long)(rank + 1) * nparts / S);
+  const int p_newx = nparts - 1;
+  const int p_newg = TV ? a.wp2 : -1;
+  const size_t stride4 = HALF;
+
+  for (int tile = 0; tile < P::TILES; tile++) {
+    const int q = tile * NT + tid;  // float4 index inside a frame: bins 2q, 2q+1
+    const bool owns = q < HALF;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 acc0 = make_float2(0.f, 0.f);
+    if (owns) {
+      const float4 *F = reinterpret_cast<const float4 *>(fdl) + q;
+      const float4 *Gp = reinterpret_cast<const float4 *>(irs) + q;
+      // walk [p_lo, p_hi) in ascending p, cutting at the FDL wrap point and around the new frames
+      int p = p_lo;
+      while (p < p_hi) {
+        if (p == p_newx || p == p_newg) {
+          p++;
+          continue;
+        }
+        int end = p_hi;
+        if (p_newx > p && p_newx < end) end = p_newx;
+        if (p_newg > p && p_newg < end) end = p_newg;
+        const int wrap = nparts - rp;  // first p whose FDL frame index wraps to 0
+        if (wrap > p && wrap < end) end = wrap;
+        const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
+        mac_segment<8>(acc, acc0, F + (size_t)frame * stride4, Gp + (size_t)p * stride4, end - p, stride4);
+        p = end;
+      }
+      if (rank == 0) {
+        // the terms that involve frames produced by this launch, from shared memory
+        const int b0 = 2 * q;
+        float2 x0 = sX[pad_idx(b0)], x1 = sX[pad_idx(b0 + 1)];
+        float4 xn = make_float4(x0.x, x0.y, x1.x, x1.y);
+        float4 gn;
+        if (TV && p_newg == p_newx) {
+          float2 g0 = sG[pad_idx(b0)], g1 = sG[pad_idx(b0 + 1)];
+          gn = make_float4(g0.x, g0.y, g1.x, g1.y);
+        } else {
+          gn = __ldcs(Gp + (size_t)p_newx * stride4);
+        }
+        cmac2(acc, xn, gn);
+        acc0.x += xn.x * gn.x;
+        acc0.y += xn.y * gn.y;
+        if (TV && p_newg != p_newx) {
+          const int frame = (rp + p_newg < nparts) ? rp + p_newg : rp + p_newg - nparts;
+          float4 fo = __ldcs(F + (size_t)frame * stride4);
+          float2 g0 = sG[pad_idx(b0)], g1 = sG[pad_idx(b0 + 1)];
+          float4 gg = make_float4(g0.x, g0.y, g1.x, g1.y);
+          cmac2(acc, fo, gg);
+          acc0.x += fo.x * gg.x;
+          acc0.y += fo.y * gg.y;
+        }
+      }
+      if (q == 0) {  // packed (DC, Nyquist) bin: component-wise product
+        acc.x = acc0.x;
+        acc.y = acc0.y;
+      }
+      if (S > 1) sP[q] = acc;
+    }
+    if (S > 1) {
+      cluster.sync();  // all partials of this tile visible cluster-wide
+      if (rank == 0 && owns) {
+        for (int r = 1; r < S; r++) {
+          const float4 *remote = cluster.map_shared_rank(sP, r);
+          float4 o = remote[q];
+          acc.x += o.x;
+          acc.y += o.y;
+          acc.z += o.z;
+          acc.w += o.w;
+        }
+      }
+      cluster.sync();  // remote reads done before anyone overwrites sP (next tile) or exits
+    }
+    if (rank == 0) {
+      if (P::TILES == 1) __syncthreads();  // every thread has consumed sX/sG before Y overwrites sX
+      // (TILES > 1: Y cannot go to sX yet; it is parked in sP-like scratch below)
+      if (owns) {
+        if (P::TILES == 1) {
+          sX[pad_idx(2 * q)] = make_float2(acc.x, acc.y);
+          sX[pad_idx(2 * q + 1)] = make_float2(acc.z, acc.w);
+        } else {
+          // park in the partial buffer area past the first HALF entries (sized for it by the host)
+          sP[HALF + q] = acc;
+        }
+      }
+    }
+  }
+  if (rank != 0) return;
+  __syncthreads();
+  if (P::TILES > 1) {
+    for (int q = tid; q < HALF; q += NT) {
+      float4 y = sP[HALF + q];
+      sX[pad_idx(2 * q)] = make_float2(y.x, y.y);
+      sX[pad_idx(2 * q + 1)] = make_float2(y.z, y.w);
+    }
+    __syncthreads();
+  }
+
+  // ---- 3. unsplit (cl_conv_kernels.h:87-100), inverse FFT, overlap-add (120-124) ------------------
+  for (int i = tid; i < PTS / 2; i += NT) {
+    if (i == 0) {
+      sX[pad_idx(0)] = rfft_dc<true>(sX[pad_idx(0)]);
+    } else {
+      float2 ci = sX[pad_idx(i)], cj = sX[pad_idx(PTS - i)];
+      rfft_pair<true>(ci, cj, __ldg(&a.w2[i]));
+      sX[pad_idx(i)] = ci;
+      sX[pad_idx(PTS - i)] = cj;
+    }
+  }
+  __syncthreads();
+  if (tid < P::FT) {
+    const int vt = tid / P::T, t = tid % P::T;
+    float2 *my = sX + vt * FftGeom<LOGP>::SMEM;
+    auto load = [&](int idx, int) { return my[pad_idx(idx)]; };
+    auto store = [&](int idx, float2 v, int) { my[pad_idx(idx)] = v; };
+    fft_run<LOGP, true, true, true>(load, store, my, a.tw, t, FftGroupSync<P::FT>());
+  }
+  __syncthreads();
+  // element m of the inverse transform holds reals (y[2m], y[2m+1]); y[0,pts) + old tail -> out,
+  // y[pts, 2pts) -> new tail
+  const float inv = 1.0f / (float)PTS;
+  float2 *out2 = reinterpret_cast<float2 *>(a.out + (size_t)ch * PTS);
+  float2 *tail2 = reinterpret_cast<float2 *>(a.tail + (size_t)ch * PTS);
+  for (int m = tid; m < PTS / 2; m += NT) {
+    float2 y = sX[pad_idx(m)], z = sX[pad_idx(m + PTS / 2)], tl = tail2[m];
+    out2[m] = make_float2((y.x + tl.x) * inv, (y.y + tl.y) * inv);
+    tail2[m] = z;
+  }
+}
+
+// IR partition transform (Clpconv::push_ir, cl_conv.cpp:353-388), all partitions of all channels in
+// one launch. grid = (nparts, channels). Partition i goes to IR frame (wp2 - i) mod nparts.
+template <int LOGP>
+__global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS)
+    pconv_push_ir_kernel(const float *ir, size_t ir_stride, float2 *irs, const float2 *__restrict__ tw,
+                         const float2 *__restrict__ w2, int nparts, int wp2) {
+  using P = PconvGeom<LOGP>;
+  constexpr int PTS = P::PTS;
+  extern __shared__ float4 smem4[];
+  float2 *sX = reinterpret_cast<float2 *>(smem4);
+  const int i = blockIdx.x, ch = blockIdx.y;
+  pconv_forward_frame<LOGP>(ir + (size_t)ch * ir_stride + (size_t)i * PTS, sX, tw, w2);
+  int frame = (wp2 - i) % nparts;
+  if (frame < 0) frame += nparts;
+  float2 *g = irs + ((size_t)ch * nparts + frame) * PTS;
+  for (int k = threadIdx.x; k < PTS; k += P::NTHREADS) g[k] = sX[pad_idx(k)];
+}
+
+}  // namespace b2f

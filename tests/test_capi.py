@@ -1,0 +1,109 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/b200fft.h declares; without a GPU nothing computes and every create fails loudly; the
+reference's own test programs compile UNCHANGED against include/ (when /root/reference is present)."""
+import ctypes as C
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "b200fft.h")
+LIBDIR = os.path.join(ROOT, "opencl_fft_b200", "lib")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2f_\w+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from opencl_fft_b200 import build
+
+    build.build()
+    return build
+
+
+def test_library_exports_every_declared_symbol(built):
+    names = _declared_symbols()
+    assert len(names) >= 30
+    L = C.CDLL(built.LIB_ENGINE)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    # and the Python binding binds exactly that set
+    from opencl_fft_b200 import _capi
+
+    assert sorted(_capi.SYMBOLS) == names
+    _capi.lib()
+
+
+def test_class_library_exports_reference_symbols(built):
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", built.LIB_CLASSES], capture_output=True, text=True).stdout
+    for sym in ["cl_fft::Clcfft::Clcfft(", "cl_fft::Clcfft::transform(", "cl_fft::Clrfft::Clrfft(",
+                "cl_fft::Clrfft::transform(std::complex<float>*, float*)", "cl_fft::cl_error_string(int)",
+                "cl_conv::Clpconv::push_ir(float*)", "cl_conv::Clpconv::convolution(float*, float*)",
+                "cl_conv::Clpconv::convolution(float*, float*, float*)", "cl_conv::Cldconv::push_ir(float*)",
+                "cl_conv::Cldconv::convolution(float*, float*)", "cl_conv::Cldconv::convolution(float*, float*, float*)",
+                "clGetDeviceIDs", "clGetDeviceInfo"]:
+        assert sym in out, sym
+
+
+def test_error_strings_and_no_silent_fallback(built):
+    import opencl_fft_b200 as e
+
+    assert e.cl_error_string(0) == "Success!"
+    assert "not found" in e.cl_error_string(1).lower()
+    if e.device_count() > 0:
+        pytest.skip("GPU present: the no-device behaviour is not observable here")
+    # no GPU: constructors record a positive error code, methods return it, nothing is computed
+    p = e.Clcfft(0, 1024, True)
+    assert p.get_error() > 0
+    x = np.ones(1024, np.complex64)
+    assert p.transform(x) > 0
+    assert np.all(x == 1)
+    msgs = []
+    c = e.Clpconv(0, 4096, 512, errs=lambda s, d: msgs.append(s), uData=None)
+    assert c.get_cl_err() > 0 and msgs
+    d = e.Cldconv(0, 256, 64, errs=lambda s, d: msgs.append(s))
+    assert d.get_cl_err() > 0
+    assert e.Clrfft(0, 4096, True).get_error() > 0
+
+
+def test_invalid_sizes_rejected(built):
+    import opencl_fft_b200 as e
+
+    if e.device_count() > 0:
+        assert e.Clcfft(0, 1000, True).get_error() == 2  # not a power of two
+        assert e.Clcfft(0, 1 << 17, True).get_error() == 3  # above the reference's int32 limit (Q13)
+        assert e.Clrfft(0, 2, True).get_error() == 2
+        assert e.Clpconv(0, 100, 512, errs=lambda s, d: None).get_cl_err() == 2  # cvs < pts: zero partitions
+    else:
+        assert e.Clcfft(0, 1000, True).get_error() > 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/test_cfft.cpp"), reason="reference sources not on this box")
+@pytest.mark.parametrize("prog", ["test_cfft", "test_rfft"])
+def test_reference_programs_compile_unchanged(built, prog, tmp_path):
+    """The reference's test programs, byte for byte, against OUR headers and libraries. They are fed on
+    stdin so that `#include "cl_fft.h"` resolves to include/cl_fft.h rather than the reference's own."""
+    exe = tmp_path / prog
+    with open(f"/root/reference/{prog}.cpp", "rb") as src:
+        res = subprocess.run(["g++", "-std=c++14", "-x", "c++", "-I", os.path.join(ROOT, "include"), "-", "-o", str(exe),
+                              "-L", LIBDIR, "-lcl_fft", "-lb200fft", f"-Wl,-rpath,{LIBDIR}"], stdin=src,
+                             capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    # keep the binary for the GPU box (oracle/_ref/ travels, stays out of git): test_dropin_gpu runs it
+    keep = os.path.join(ROOT, "oracle", "_ref")
+    os.makedirs(keep, exist_ok=True)
+    shutil.copy(exe, os.path.join(keep, prog + "_b200"))
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    import opencl_fft_b200 as e
+
+    if e.device_count() == 0:
+        assert run.returncode != 0 and "failed to find an OpenCL device" in run.stdout

@@ -1,0 +1,165 @@
+"""GPU parity of the FFT path, through the C ABI (opencl_fft_b200 -> libb200fft.so), against the oracle
+(oracle/ref_cpu.c), the golden vectors produced by the real reference, and float64 ground truth.
+Tolerance: relative L2 <= 1e-5 (BASELINE.json north_star); measured values are ~1e-7."""
+import numpy as np
+import pytest
+
+from conftest import TOL, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def crand(rng, *shape):
+    return (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(np.complex64)
+
+
+def test_kat_cfft(eng, golden):
+    f, i = eng.Clcfft(0, 16, True), eng.Clcfft(0, 16, False)
+    assert f.get_error() == 0 and i.get_error() == 0
+    x = golden["kat_cfft_in"].copy()
+    assert f.transform(x) == 0
+    want = np.zeros(16, np.complex64)
+    want[1], want[15] = -0.5j, 0.5j
+    assert np.abs(x - want).max() < 1e-6
+    assert rel_l2(x, golden["kat_cfft_spec"]) < TOL
+    assert i.transform(x) == 0
+    assert np.abs(x - golden["kat_cfft_in"]).max() < 1e-6
+
+
+def test_kat_rfft(eng, golden):
+    f, i = eng.Clrfft(0, 16, True), eng.Clrfft(0, 16, False)
+    r = golden["kat_rfft_in"].copy()
+    spec = np.zeros(8, np.complex64)
+    assert f.transform(spec, r) == 0  # out-of-place form, as test_rfft.cpp:64 uses it
+    want = np.zeros(8, np.complex64)
+    want[0], want[1] = 0.5 + 0.5j, -1j
+    assert np.abs(spec - want).max() < 1e-6
+    back = np.zeros(16, np.float32)
+    assert i.transform(spec, back) == 0
+    assert np.abs(back - golden["kat_rfft_in"]).max() < 1e-6
+    assert np.abs(spec.view(np.float32) - back).max() == 0  # c is overwritten too (cl_fft.cpp:290-293)
+
+
+@pytest.mark.parametrize("logn", range(1, 17))
+@pytest.mark.parametrize("fwd", [True, False])
+def test_cfft_vs_oracle_all_sizes(eng, port, logn, fwd):
+    N = 1 << logn
+    rng = np.random.default_rng(1001 + logn)
+    x = crand(rng, N)
+    p = eng.Clcfft(0, N, fwd)
+    assert p.get_error() == 0
+    y = x.copy()
+    assert p.transform(y) == 0
+    assert rel_l2(y, port.cfft(x, fwd)) < TOL
+    truth = np.fft.fft(x.astype(np.complex128)) / N if fwd else np.fft.ifft(x.astype(np.complex128)) * N
+    assert rel_l2(y, truth) < 2e-6
+
+
+@pytest.mark.parametrize("logn,batch", [(1, 700), (4, 1000), (5, 333), (6, 257), (8, 129), (10, 67), (12, 9), (13, 5), (14, 3), (15, 5), (16, 3)])
+def test_cfft_batched(eng, port, logn, batch):
+    N = 1 << logn
+    rng = np.random.default_rng(logn)
+    x = crand(rng, batch, N)
+    p = eng.Clcfft(0, N, True, max_batch=batch)
+    y = x.copy()
+    assert p.transform(y.reshape(-1)) == 0
+    truth = np.fft.fft(x.astype(np.complex128), axis=1) / N
+    assert rel_l2(y, truth) < 2e-6
+    for b in (0, batch // 2, batch - 1):
+        assert rel_l2(y[b], port.cfft(x[b], True)) < TOL
+    # round trip through the inverse plan
+    q = eng.Clcfft(0, N, False, max_batch=batch)
+    assert q.transform(y.reshape(-1)) == 0
+    assert rel_l2(y, x) < 2e-6
+    assert p.transform(np.zeros((batch + 1) * N, np.complex64)) == 6  # over max_batch
+
+
+def test_golden_cfft_rfft(eng, golden):
+    g = golden
+    for fwd, key in ((True, "cfft1024_fwd"), (False, "cfft1024_inv")):
+        y = g["cfft1024_in"].copy()
+        assert eng.Clcfft(0, 1024, fwd).transform(y) == 0
+        assert rel_l2(y, g[key]) < TOL
+    c = g["rfft4096_in"].copy().view(np.complex64)
+    assert eng.Clrfft(0, 4096, True).transform(c) == 0  # in-place form
+    assert rel_l2(c, g["rfft4096_fwd"]) < TOL
+    assert eng.Clrfft(0, 4096, False).transform(c) == 0
+    assert rel_l2(c.view(np.float32), g["rfft4096_back"]) < TOL
+    assert np.abs(c.view(np.float32) - g["rfft4096_in"]).max() < 1e-5
+    c = g["rfft65536_in"].copy().view(np.complex64)
+    assert eng.Clrfft(0, 65536, True).transform(c) == 0
+    assert rel_l2(c, g["rfft65536_fwd"]) < TOL
+
+
+@pytest.mark.parametrize("logs", range(2, 18))
+def test_rfft_vs_oracle_all_sizes(eng, port, logs):
+    size = 1 << logs
+    rng = np.random.default_rng(1002 + logs)
+    r = rng.uniform(-1, 1, size).astype(np.float32)
+    f, i = eng.Clrfft(0, size, True), eng.Clrfft(0, size, False)
+    assert f.get_error() == 0 and i.get_error() == 0
+    c = np.zeros(size // 2, np.complex64)
+    assert f.transform(c, r.copy()) == 0
+    want = port.rfft_fwd(r)
+    assert rel_l2(c, want) < TOL
+    # quirk Q3: bin size/4 is the conjugate of the true value
+    X = np.fft.rfft(r.astype(np.float64))
+    if size >= 8:
+        assert abs(c[size // 4] - np.conj(2 * X[size // 4] / size)) < 1e-5
+    back = np.zeros(size, np.float32)
+    assert i.transform(c, back) == 0
+    assert rel_l2(back, port.rfft_inv(want)) < TOL
+    assert np.abs(back - r).max() < 2e-5
+
+
+def test_rfft_batched_cfg5_shape_properties(eng):
+    """BASELINE config 5a shape (65536-point real FFT), a 64-channel slice: properties that hold at any
+    size -- round trip, linearity, Parseval in the reference's scaling."""
+    size, ch = 65536, 64
+    rng = np.random.default_rng(6000)
+    a = rng.uniform(-1, 1, (ch, size)).astype(np.float32)
+    b = rng.uniform(-1, 1, (ch, size)).astype(np.float32)
+    f, i = eng.Clrfft(0, size, True, max_batch=ch), eng.Clrfft(0, size, False, max_batch=ch)
+    A, B, AB = (np.zeros((ch, size // 2), np.complex64) for _ in range(3))
+    assert f.transform(A.reshape(-1), a.reshape(-1).copy()) == 0
+    assert f.transform(B.reshape(-1), b.reshape(-1).copy()) == 0
+    assert f.transform(AB.reshape(-1), (a + 2 * b).reshape(-1).copy()) == 0
+    assert rel_l2(AB, A + 2 * B) < 2e-6  # linearity
+    # Parseval: sum x^2 / size = DC^2 + Nyq^2 + sum_{k>=1} |S_k|^2 / 2 in the reference's scaling
+    lhs = (a.astype(np.float64) ** 2).sum(axis=1) / size
+    S = A.astype(np.complex128)
+    rhs = S[:, 0].real ** 2 + S[:, 0].imag ** 2 + 0.5 * (np.abs(S[:, 1:]) ** 2).sum(axis=1)
+    assert np.abs(lhs - rhs).max() / lhs.max() < 1e-5
+    back = np.zeros((ch, size), np.float32)
+    assert i.transform(A.reshape(-1), back.reshape(-1)) == 0
+    assert rel_l2(back, a) < 2e-6  # round trip
+    truth = np.fft.rfft(a[7].astype(np.float64)) * 2 / size
+    got = np.zeros(size // 2, np.complex64)
+    f1 = eng.Clrfft(0, size, True)
+    assert f1.transform(got, a[7].copy()) == 0
+    k = np.r_[1:size // 4, size // 4 + 1:size // 2]
+    assert rel_l2(got[k], truth[k]) < 2e-6
+
+
+def test_device_pointer_api_matches_host_api(eng):
+    import torch
+
+    N, batch = 1024, 4096
+    rng = np.random.default_rng(1)
+    x = crand(rng, batch, N)
+    p = eng.Clcfft(0, N, True, max_batch=batch)
+    want = x.copy()
+    assert p.transform(want.reshape(-1)) == 0
+    d_in = torch.from_numpy(x.view(np.float32)).cuda()
+    d_out = torch.empty_like(d_in)
+    assert p.transform_dev(d_in, d_out, batch) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().view(np.complex64), want)  # same kernel, same bits
+    assert p.transform_dev(d_in, d_in, batch) == 0  # in place
+    torch.cuda.synchronize()
+    assert np.array_equal(d_in.cpu().numpy().view(np.complex64), want)
+    # determinism
+    d2 = torch.from_numpy(x.view(np.float32)).cuda()
+    assert p.transform_dev(d2, d2, batch) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(d2, d_in)

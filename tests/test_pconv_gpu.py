@@ -1,0 +1,196 @@
+"""GPU parity of the partitioned convolution (Clpconv) through the C ABI against the oracle, the golden
+vectors of the real reference, and float64 models. Streaming over enough blocks to wrap both rings."""
+import numpy as np
+import pytest
+
+from conftest import TOL, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def run_stream(conv, x, x2=None):
+    """x: [nb][channels][pts] -> y same shape"""
+    y = np.zeros_like(x)
+    for t in range(x.shape[0]):
+        rc = conv.convolution(y[t], x[t]) if x2 is None else conv.convolution(y[t], x[t], x2[t])
+        assert rc == 0
+    return y
+
+
+def test_golden_cfg3(eng, golden):
+    g = golden
+    c = eng.Clpconv(0, 96000, 512)
+    assert c.get_cl_err() == 0 and c.nparts == 187
+    assert c.push_ir(g["pconv_cfg3_ir"]) == 0
+    y = run_stream(c, g["pconv_cfg3_in"][:, None, :])[:, 0]
+    assert rel_l2(y, g["pconv_cfg3_out"]) < TOL
+
+
+def test_golden_small_static_and_time_varying(eng, golden):
+    g = golden
+    c = eng.Clpconv(0, 1000, 64)
+    assert c.nparts == 15
+    assert c.push_ir(g["pconv_small_ir"]) == 0
+    y = run_stream(c, g["pconv_small_in"][:, None, :])[:, 0]
+    assert rel_l2(y, g["pconv_small_out"]) < TOL
+    c = eng.Clpconv(0, 1000, 64)
+    y = run_stream(c, g["pconv_small_in"][:, None, :], g["pconv_small_in2"][:, None, :])[:, 0]
+    assert rel_l2(y, g["pconv_small_tv_out"]) < TOL
+
+
+@pytest.mark.parametrize("pts", [2, 4, 16, 32, 64, 256, 512, 1024, 2048, 4096])
+def test_static_vs_oracle_all_partition_sizes(eng, port, pts):
+    nparts = 5
+    cvs = nparts * pts + pts // 2  # truncating division must drop the half partition
+    nb = 2 * nparts + 3
+    rng = np.random.default_rng(pts)
+    ir = rng.standard_normal(cvs).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, 1, pts)).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts)
+    assert c.get_cl_err() == 0 and c.nparts == nparts
+    o = port.pconv(cvs, pts)
+    assert c.push_ir(ir) == 0
+    o.push_ir(ir)
+    # white box: the IR spectra ring has the reference's frame order and values
+    assert rel_l2(c.read_spectra(2), o.spec2()) < TOL
+    y = run_stream(c, x)[:, 0]
+    want = np.stack([o.convolution(b[0]) for b in x])
+    assert rel_l2(y, want) < TOL
+    assert rel_l2(c.read_spectra(1), o.spec1()) < TOL  # frequency-domain delay line
+
+
+@pytest.mark.parametrize("pts,nparts", [(16, 1), (16, 2), (64, 7), (512, 9)])
+def test_time_varying_vs_oracle(eng, port, pts, nparts):
+    cvs = nparts * pts
+    nb = 3 * nparts + 2
+    rng = np.random.default_rng(pts + nparts)
+    x = rng.uniform(-1, 1, (nb, 1, pts)).astype(np.float32)
+    x2 = rng.uniform(-1, 1, (nb, 1, pts)).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts)
+    o = port.pconv(cvs, pts)
+    y = run_stream(c, x, x2)[:, 0]
+    want = np.stack([o.convolution(a[0], b[0]) for a, b in zip(x, x2)])
+    assert rel_l2(y, want) < TOL
+    assert rel_l2(c.read_spectra(2), o.spec2()) < TOL
+
+
+def test_mixed_static_then_time_varying(eng, port):
+    """push_ir, a few static blocks, then time-varying blocks re-recording the IR ring (Q12)."""
+    cvs, pts = 640, 64
+    rng = np.random.default_rng(12)
+    ir = rng.standard_normal(cvs).astype(np.float32)
+    x = rng.uniform(-1, 1, (30, 1, pts)).astype(np.float32)
+    x2 = rng.uniform(-1, 1, (30, 1, pts)).astype(np.float32)
+    c, o = eng.Clpconv(0, cvs, pts), port.pconv(cvs, pts)
+    c.push_ir(ir)
+    o.push_ir(ir)
+    got, want = [], []
+    for t in range(30):
+        y = np.zeros((1, pts), np.float32)
+        if t < 8 or t >= 20:
+            assert c.convolution(y, x[t]) == 0
+            want.append(o.convolution(x[t, 0]))
+        else:
+            assert c.convolution(y, x[t], x2[t]) == 0
+            want.append(o.convolution(x[t, 0], x2[t, 0]))
+        got.append(y[0])
+    assert rel_l2(np.stack(got), np.stack(want)) < TOL
+
+
+@pytest.mark.parametrize("channels", [1, 3, 40, 300])
+def test_multichannel_matches_per_channel_oracle(eng, port, channels):
+    """channels selects the cluster split: 1 -> 8 CTAs per channel, 40 -> 8, 300 -> 1."""
+    cvs, pts, nb = 3200, 128, 30
+    rng = np.random.default_rng(channels)
+    ir = rng.standard_normal((channels, cvs)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, channels, pts)).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts, channels=channels)
+    assert c.push_ir(ir) == 0
+    y = run_stream(c, x)
+    for ch in sorted({0, channels // 2, channels - 1}):
+        o = port.pconv(cvs, pts)
+        o.push_ir(ir[ch])
+        want = np.stack([o.convolution(x[t, ch]) for t in range(nb)])
+        assert rel_l2(y[:, ch], want) < TOL
+    # determinism: a second object fed the same stream gives the same bits
+    c2 = eng.Clpconv(0, cvs, pts, channels=channels)
+    c2.push_ir(ir)
+    assert np.array_equal(run_stream(c2, x), y)
+
+
+def test_float64_model_with_quirk_q5(eng):
+    """Against float64: exact linear convolution except half-weight DC/Nyquist per frame product."""
+    cvs, pts, nb = 4096, 512, 20
+    rng = np.random.default_rng(5)
+    ir = rng.standard_normal(cvs).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, 1, pts)).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts)
+    c.push_ir(ir)
+    y = run_stream(c, x)[:, 0].ravel()
+    H = [np.fft.rfft(np.r_[ir[i * pts:(i + 1) * pts].astype(np.float64), np.zeros(pts)]) for i in range(cvs // pts)]
+    X = [np.fft.rfft(np.r_[b[0].astype(np.float64), np.zeros(pts)]) for b in x]
+    out, tail = [], np.zeros(pts)
+    for t in range(nb):
+        Y = sum(X[t - a] * H[a] for a in range(len(H)) if t - a >= 0)
+        Y[0] *= 0.5
+        Y[-1] *= 0.5
+        yy = np.fft.irfft(Y)
+        out.append(yy[:pts] + tail)
+        tail = yy[pts:]
+    assert rel_l2(y, np.concatenate(out)) < 2e-6
+
+
+def test_cfg5_shape_properties(eng, port):
+    """BASELINE config 5b shape (480000-tap IR -> 937 partitions of 512), a 16-channel slice: linearity and
+    time invariance hold at full size; one channel is also checked block by block against the oracle."""
+    cvs, pts, ch, nb = 480000, 512, 16, 6
+    rng = np.random.default_rng(7000)
+    n = np.arange(cvs)
+    ir = (rng.standard_normal((ch, cvs)) * np.exp(-6.9078 * n / cvs)).astype(np.float32)
+    ir /= np.linalg.norm(ir, axis=1, keepdims=True)
+    xa = rng.uniform(-1, 1, (nb, ch, pts)).astype(np.float32)
+    xb = rng.uniform(-1, 1, (nb, ch, pts)).astype(np.float32)
+
+    def run(x):
+        c = eng.Clpconv(0, cvs, pts, channels=ch)
+        assert c.get_cl_err() == 0 and c.nparts == 937
+        assert c.push_ir(ir) == 0
+        return run_stream(c, x)
+
+    ya, yb, yab = run(xa), run(xb), run(xa + 0.5 * xb)
+    assert rel_l2(yab, ya + 0.5 * yb) < 2e-6
+    # time invariance: delaying the input by one block delays the output by one block
+    xd = np.concatenate([np.zeros((1, ch, pts), np.float32), xa[:-1]])
+    yd = run(xd)
+    assert rel_l2(yd[1:], ya[:-1]) < 2e-6
+    o = port.pconv(cvs, pts)
+    o.push_ir(ir[3])
+    want = np.stack([o.convolution(xa[t, 3]) for t in range(nb)])
+    assert rel_l2(ya[:, 3], want) < TOL
+
+
+def test_reset_and_device_api(eng):
+    import torch
+
+    cvs, pts, ch, nb = 2048, 256, 8, 12
+    rng = np.random.default_rng(3)
+    ir = rng.standard_normal((ch, cvs)).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, ch, pts)).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts, channels=ch)
+    c.push_ir(ir)
+    y = run_stream(c, x)
+    assert c.reset() == 0
+    d = eng.Clpconv(0, cvs, pts, channels=ch)
+    d_ir = torch.from_numpy(ir).cuda()
+    assert d.push_ir_dev(d_ir, cvs) == 0
+    d_x = torch.from_numpy(x).cuda()
+    d_y = torch.zeros_like(d_x)
+    for t in range(nb):
+        assert c.convolution_dev(d_y[t], d_x[t]) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_y.cpu().numpy(), y)  # after reset, same stream -> same bits
+    d_y2 = torch.zeros_like(d_x)
+    for t in range(nb):
+        assert d.convolution_dev(d_y2[t], d_x[t]) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_y2.cpu().numpy(), y)  # device-side push_ir == host-side push_ir
