@@ -29,7 +29,7 @@ def test_golden_cfg4_and_time_varying(eng, golden):
 def test_vs_oracle(eng, port, irsize, vsize):
     nb = 2 * (irsize // vsize) + 5 if irsize // vsize < 40 else 50
     rng = np.random.default_rng(irsize + vsize)
-    ir = rng.standard_normal(irsize).astype(np.float32) / np.sqrt(irsize)
+    ir = (rng.standard_normal(irsize) / np.sqrt(irsize)).astype(np.float32)
     x = rng.uniform(-1, 1, (nb, vsize)).astype(np.float32)
     c, o = eng.Cldconv(0, irsize, vsize), port.dconv(irsize, vsize)
     assert c.push_ir(ir) == 0
@@ -47,9 +47,9 @@ def test_vs_oracle(eng, port, irsize, vsize):
 def test_time_varying_vs_oracle(eng, port, irsize, vsize):
     nb = 3 * (irsize // vsize + 1) + 2
     rng = np.random.default_rng(irsize)
-    ir = rng.standard_normal(irsize).astype(np.float32) / np.sqrt(irsize)
+    ir = (rng.standard_normal(irsize) / np.sqrt(irsize)).astype(np.float32)
     x = rng.uniform(-1, 1, (nb, vsize)).astype(np.float32)
-    x2 = rng.uniform(-1, 1, (nb, vsize)).astype(np.float32) / np.sqrt(irsize)
+    x2 = (rng.uniform(-1, 1, (nb, vsize)) / np.sqrt(irsize)).astype(np.float32)
     c, o = eng.Cldconv(0, irsize, vsize), port.dconv(irsize, vsize)
     c.push_ir(ir)
     o.push_ir(ir)
