@@ -1,0 +1,505 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload pconv|rfft]
+
+Headline workload (BASELINE.json configs[4], "metric" second half): partitioned convolution with 10 s
+impulse responses (480,000 taps -> 937 partitions of 512 samples), 1024 channels per GPU, one distinct
+IR per channel. One "step" = one 512-sample streaming block for every channel (one fused kernel launch).
+  value = real-time channels @ 48 kHz = channels * (512 / 48000 s) / t_step          (whole job, all GPUs)
+`--workload rfft` makes the other half of the metric (batched 1024 x 65536-point real FFT, GB/s) the
+headline instead; by default it is reported under "secondary" together with the batched 1024-point
+complex FFT and the direct convolution of config 4.
+
+Multi-GPU (torchrun, one rank per GPU): channels are sharded, every rank owns all state of its channels,
+there is no data-path collective; NCCL carries only the barrier and the max-over-ranks of the step time.
+Scaling is weak: 1024 channels per GPU.
+
+`--impl reference` times the reference's own implementation on the host CPU cores: the unmodified
+reference sources compiled against oracle/minicl when oracle/_ref/libclfft_ref.so is present
+(kind "reference"), else the C restatement (kind "port"); one reference object per channel, one channel
+per thread. That leg and the `cpu_baseline` object are the only places the oracle is executed here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 48000.0
+PTS = 512
+CVS = 480000  # 10 s at 48 kHz -> 937 partitions (truncating)
+CHANNELS_PER_GPU = 1024
+RFFT_SIZE = 65536
+RFFT_BATCH = 1024
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def ncu_traffic(key):
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture, or None"""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(key)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def __enter__(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier():
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def event_time_ms(fn, steps, warmup):
+    """W untimed calls, then exactly K calls bracketed by barrier+synchronize, timed with CUDA events on the
+    launching (current) stream. Returns total ms of this rank."""
+    import torch
+
+    for i in range(warmup):
+        fn(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def synth_ir_dev(channels, cvs, seed):
+    """decaying-noise IRs (-60 dB over the IR length), L2-normalised, generated on the device"""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    n = torch.arange(cvs, device="cuda", dtype=torch.float32)
+    env = torch.exp(-6.9078 * n / cvs)
+    ir = torch.randn(channels, cvs, generator=g, device="cuda") * env
+    ir /= ir.norm(dim=1, keepdim=True)
+    return ir.contiguous()
+
+
+def bench_pconv(eng, local, rank, world, steps, warmup, channels=CHANNELS_PER_GPU, cvs=CVS, pts=PTS, e2e=True):
+    import numpy as np
+    import torch
+
+    from opencl_fft_b200.shard import max_over_ranks
+
+    conv = eng.Clpconv(local, cvs, pts, channels=channels)
+    if conv.get_cl_err():
+        raise RuntimeError("Clpconv: " + eng.cl_error_string(conv.get_cl_err()) + " " + eng.last_cuda_error())
+    ir = synth_ir_dev(channels, cvs, 7000 + rank)
+    assert conv.push_ir_dev(ir, cvs) == 0
+    torch.cuda.synchronize()
+    del ir
+    nring = 8
+    g = torch.Generator(device="cuda").manual_seed(3000 + rank)
+    x = (torch.rand(nring, channels, pts, generator=g, device="cuda") * 2 - 1).contiguous()
+    y = torch.empty(channels, pts, device="cuda")
+
+    def step(i):
+        rc = conv.convolution_dev(y, x[i % nring])
+        assert rc == 0, rc
+
+    with ClockSampler(local) as clk:
+        ms = event_time_ms(step, steps, warmup)
+    ms_max = max_over_ranks(ms)
+    nparts = conv.nparts
+    bytes_per_launch = channels * 8 * pts * (2 * nparts + 3)
+    res = {
+        "ms_per_step": ms_max / steps,
+        "ms_per_step_rank": ms / steps,
+        "channels_per_gpu": channels,
+        "nparts": nparts,
+        "bytes_per_launch": bytes_per_launch,
+        "clocks": clk.summary(),
+        "launches": steps,
+    }
+    # end to end through the reference-facing host API: pinned host buffers in, pinned host buffers out,
+    # H2D + kernel + D2H inside every timed call (the call is synchronous like the reference's)
+    if e2e:
+        hx = torch.empty(nring, channels, pts).pin_memory()
+        hx.copy_(x.cpu())
+        hy = torch.empty(channels, pts).pin_memory()
+        hx_np, hy_np = hx.numpy(), hy.numpy()
+        conv.reset()
+        for i in range(warmup):
+            assert conv.convolution(hy_np, hx_np[i % nring]) == 0
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            assert conv.convolution(hy_np, hx_np[(warmup + i) % nring]) == 0
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        e2e_ms = max_over_ranks((t1 - t0) * 1e3)
+        res["e2e_ms_per_step"] = e2e_ms / steps
+        res["h2d_bytes_per_step"] = channels * pts * 4
+        res["d2h_bytes_per_step"] = channels * pts * 4
+        # the host path and the device path run the same kernel on the same state: same bits
+        conv.reset()
+        conv2_out = torch.empty(channels, pts, device="cuda")
+        assert conv.convolution(hy_np, hx_np[0]) == 0
+        conv.reset()
+        assert conv.convolution_dev(conv2_out, x[0]) == 0
+        torch.cuda.synchronize()
+        res["e2e_matches_device_path"] = bool(np.array_equal(conv2_out.cpu().numpy(), hy_np))
+    conv.close()
+    return res
+
+
+def bench_rfft(eng, local, rank, world, steps, warmup, size=RFFT_SIZE, batch=RFFT_BATCH, e2e=False):
+    import torch
+
+    from opencl_fft_b200.shard import max_over_ranks
+
+    plan = eng.Clrfft(local, size, True, max_batch=batch)
+    if plan.get_error():
+        raise RuntimeError("Clrfft: " + eng.cl_error_string(plan.get_error()))
+    g = torch.Generator(device="cuda").manual_seed(6000 + rank)
+    nbuf = 3  # 3 x 256 MiB in + 3 x 256 MiB out: successive steps never find their data in the 126 MB L2
+    x = (torch.rand(nbuf, batch, size, generator=g, device="cuda") * 2 - 1).contiguous()
+    y = torch.empty(nbuf, batch, size, device="cuda")
+
+    def step(i):
+        assert plan.transform_dev(x[i % nbuf], y[i % nbuf], batch) == 0
+
+    with ClockSampler(local) as clk:
+        ms = event_time_ms(step, steps, warmup)
+    ms_max = max_over_ranks(ms)
+    bytes_per_step = batch * 8 * size  # 4*size in + 8*(size/2) out
+    res = {"ms_per_step": ms_max / steps, "bytes_per_step": bytes_per_step, "clocks": clk.summary(),
+           "batch": batch, "size": size}
+    if e2e:
+        hx = torch.empty(batch, size).pin_memory()
+        hx.copy_(x[0].cpu())
+        hc = torch.empty(batch, size).pin_memory()
+        a, c = hx.numpy().reshape(-1), hc.numpy().reshape(-1).view("complex64")
+        for _ in range(2):
+            assert plan.transform(c, a) == 0
+        barrier()
+        n = max(3, min(steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            assert plan.transform(c, a) == 0
+        t1 = time.perf_counter()
+        res["e2e_ms_per_step"] = max_over_ranks((t1 - t0) * 1e3) / n
+        res["h2d_bytes_per_step"] = batch * size * 4
+        res["d2h_bytes_per_step"] = batch * size * 4
+    plan.close()
+    return res
+
+
+def bench_cfft1024(eng, local, steps, warmup):
+    import torch
+
+    N, batch = 1024, 65536  # 512 MiB in, 512 MiB out
+    plan = eng.Clcfft(local, N, True, max_batch=1)
+    x = torch.randn(2, batch, N, 2, device="cuda")
+    y = torch.empty_like(x)
+
+    def step(i):
+        assert plan.transform_dev(x[i % 2], y[i % 2], batch) == 0
+
+    ms = event_time_ms(step, steps, warmup)
+    plan.close()
+    return {"ms_per_step": ms / steps, "bytes_per_step": batch * 16 * N}
+
+
+def bench_dconv(eng, local, steps, warmup):
+    import torch
+
+    irsize, vsize, ch, nblocks = 4096, 256, 64, 375  # config 4, 2 s of audio per launch
+    conv = eng.Cldconv(local, irsize, vsize, channels=ch, max_blocks=1)
+    ir = torch.randn(ch, irsize, device="cuda") / 64
+    assert conv.push_ir_dev(ir, irsize) == 0
+    x = torch.rand(ch, nblocks * vsize, device="cuda") * 2 - 1
+    y = torch.empty_like(x)
+
+    def step(i):
+        assert conv.convolution_dev(y, x, nblocks=nblocks) == 0
+
+    ms = event_time_ms(step, steps, warmup)
+    # single-block latency (the streaming call of the reference): one 256-sample block, 64 channels
+    xb = x[:, :vsize].contiguous()
+    yb = torch.empty_like(xb)
+
+    def step1(i):
+        assert conv.convolution_dev(yb, xb, nblocks=1) == 0
+
+    ms1 = event_time_ms(step1, 50, 5)
+    conv.close()
+    flop = 2.0 * irsize * vsize * nblocks * ch
+    return {"ms_per_step": ms / steps, "flop_per_step": flop, "single_block_us": ms1 / 50 * 1e3}
+
+
+def cpu_baseline_pconv(threads, cvs=CVS, pts=PTS, blocks=None):
+    """The reference's own implementation on the host cores: `threads` channels (one per thread)."""
+    import numpy as np
+
+    import oracle
+
+    impl = oracle.best()
+    nparts = cvs // pts
+    if blocks is None:
+        blocks = 160  # ~15 s of CPU work on 16 cores
+    rng = np.random.default_rng(7000)
+    n = np.arange(cvs)
+    ir = (rng.standard_normal((threads, cvs)) * np.exp(-6.9078 * n / cvs)).astype(np.float32)
+    x = rng.uniform(-1, 1, (threads, blocks * pts)).astype(np.float32)
+    secs, _ = impl.pconv_run(cvs, pts, ir, x, threads)
+    t_step = secs / blocks
+    return {
+        "value": threads * (pts / SR) / t_step,
+        "unit": "realtime_channels_48k",
+        "cores": threads,
+        "kind": impl.kind,
+        "sample": f"{threads} channels x {blocks} blocks of {pts} samples, {nparts} partitions each, "
+                  f"{secs:.2f} s wall",
+        "seconds": secs,
+    }
+
+
+def cpu_baseline_rfft(threads, size=RFFT_SIZE, batch=None):
+    import numpy as np
+
+    import oracle
+
+    impl = oracle.best()
+    if batch is None:
+        batch = 128 * threads  # ~10 s of CPU work
+    rng = np.random.default_rng(6000)
+    x = rng.uniform(-1, 1, (batch, size)).astype(np.float32)
+    secs, _ = impl.rfft_run(x, True, threads)
+    return {"value": batch * 8 * size / secs / 1e9, "unit": "GB/s", "cores": threads, "kind": impl.kind,
+            "sample": f"{batch} transforms of {size} real points, {secs:.2f} s wall", "seconds": secs}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation, same metric/unit/config as our arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    fn = cpu_baseline_pconv if args.workload == "pconv" else cpu_baseline_rfft
+    small = {"blocks": 16} if args.workload == "pconv" else {"batch": 16 * threads}
+    for _ in range(args.warmup):
+        fn(threads, **small)
+    vals, secs = [], 0.0
+    for _ in range(args.steps):
+        r = fn(threads, **small)
+        vals.append(r["value"])
+        secs += r["seconds"]
+    v = statistics.median(vals)
+    line = {
+        "impl": "reference",
+        "metric": "pconv_realtime_channels_48k" if args.workload == "pconv" else "batched_rfft_GBps",
+        "value": v, "unit": r["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload),
+        "cpu_baseline": {"value": v, "unit": r["unit"], "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": v, "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(workload):
+    if workload == "pconv":
+        return {"workload": "BASELINE configs[4] (partitioned-conv half): 1024 channels per GPU x 480000-tap (10 s) IRs, "
+                            "512-sample partitions (937), one 512-sample block per channel per step",
+                "channels_per_gpu": CHANNELS_PER_GPU, "ir_taps": CVS, "partition": PTS, "sample_rate": 48000,
+                "l2_policy": "working set 7.9 GB per step >> 126 MB L2, no flush needed",
+                "parallelism": "channels sharded across GPUs, no collective"}
+    return {"workload": "BASELINE configs[4] (FFT half): 1024 x 65536-point real FFT per GPU, forward",
+            "batch_per_gpu": RFFT_BATCH, "size": RFFT_SIZE,
+            "l2_policy": "3 rotating input/output buffer pairs of 256 MiB each, larger than the 126 MB L2",
+            "parallelism": "transform batch sharded across GPUs, no collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="pconv", choices=["pconv", "rfft"])
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+
+    import opencl_fft_b200 as eng  # raises if the CUDA library is not built: no fallback
+
+    rank, world, local = dist_setup(args.gpus)
+    peak, peak_src, sm_max = measured_peaks()
+
+    if args.workload == "pconv":
+        r = bench_pconv(eng, local, rank, world, args.steps, args.warmup)
+        t_step = r["ms_per_step"] * 1e-3
+        channels_total = r["channels_per_gpu"] * world
+        value = channels_total * (PTS / SR) / t_step
+        unit, metric = "realtime_channels_48k", "pconv_realtime_channels_48k"
+        achieved = r["bytes_per_launch"] / (r["ms_per_step_rank"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "pconv_step_kernel<9,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic("pconv_step_bytes_per_launch"),
+                "algorithmic_bytes_per_launch": r["bytes_per_launch"], "peak_source": peak_src}
+        e2e_v = channels_total * (PTS / SR) / (r["e2e_ms_per_step"] * 1e-3)
+        e2e = {"value": e2e_v, "unit": unit, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": r["d2h_bytes_per_step"], "ms_per_step": r["e2e_ms_per_step"],
+               "same_bits_as_device_path": r["e2e_matches_device_path"]}
+        launches = r["launches"]
+    else:
+        r = bench_rfft(eng, local, rank, world, args.steps, args.warmup, e2e=True)
+        t_step = r["ms_per_step"] * 1e-3
+        value = r["bytes_per_step"] * world / t_step / 1e9
+        unit, metric = "GB/s", "batched_rfft_GBps"
+        achieved = r["bytes_per_step"] / t_step / 1e9
+        roof = {"bound": "hbm", "kernel": "large_cols_kernel + large_rows_kernel + rfft_split_kernel", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("rfft65536_bytes_per_step"),
+                "algorithmic_bytes_per_launch": r["bytes_per_step"], "peak_source": peak_src}
+        e2e_v = r["bytes_per_step"] * world / (r["e2e_ms_per_step"] * 1e-3) / 1e9
+        e2e = {"value": e2e_v, "unit": unit, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": r["d2h_bytes_per_step"], "ms_per_step": r["e2e_ms_per_step"]}
+        launches = args.steps * 17  # per step: 8 chunks x (cols + rows) + split
+
+    secondary = {}
+    if not args.no_secondary and rank == 0 and world == 1:
+        k = max(5, min(args.steps, 20))
+        if args.workload == "pconv":
+            f = bench_rfft(eng, local, rank, 1, k, 3)
+            gbs = f["bytes_per_step"] / (f["ms_per_step"] * 1e-3) / 1e9
+            secondary["batched_rfft_65536x1024"] = {"value": gbs, "unit": "GB/s", "ms_per_step": f["ms_per_step"],
+                                                    "roofline_frac": gbs / peak}
+        c = bench_cfft1024(eng, local, k, 3)
+        gbs = c["bytes_per_step"] / (c["ms_per_step"] * 1e-3) / 1e9
+        secondary["batched_cfft_1024x65536"] = {"value": gbs, "unit": "GB/s", "ms_per_step": c["ms_per_step"],
+                                                "roofline_frac": gbs / peak}
+        d = bench_dconv(eng, local, k, 3)
+        tf = d["flop_per_step"] / (d["ms_per_step"] * 1e-3) / 1e12
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        secondary["dconv_4096x256x64ch"] = {"value": tf, "unit": "TFLOP/s fp32", "ms_per_step": d["ms_per_step"],
+                                            "fp32_peak_nominal": fp32_peak, "fp32_frac": tf / fp32_peak,
+                                            "realtime_channels_48k": 64 * (375 * 256 / SR) / (d["ms_per_step"] * 1e-3),
+                                            "single_block_latency_us": d["single_block_us"]}
+
+    cpu = None
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        cpu = cpu_baseline_pconv(threads) if args.workload == "pconv" else cpu_baseline_rfft(threads)
+        cpu.pop("seconds", None)
+
+    if rank == 0:
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload),
+            "clocks": r["clocks"], "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if secondary:
+            line["secondary"] = secondary
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
