@@ -122,8 +122,9 @@ struct FftGeom {
 // __syncthreads()). `t` is this thread's index within the transform, in [0, T).
 // FIRST_INPLACE / LAST_INPLACE: the load functor reads / the store functor writes the very `sm` the
 // engine works in, so the pass needs the gather-before-scatter barrier it otherwise skips.
-template <int LOGN, int P, bool INV, bool FIRST_INPLACE, bool LAST_INPLACE, class Load, class Store, class Sync>
-__device__ __forceinline__ void fft_pass(Load &load, Store &store, float2 *sm, const float2 *__restrict__ tw, int t,
+template <int LOGN, int P, bool INV, bool FIRST_INPLACE, bool LAST_INPLACE, bool TW_SMEM, class Load, class Store,
+          class Sync>
+__device__ __forceinline__ void fft_pass(Load &load, Store &store, float2 *sm, const float2 *tw, int t,
                                          Sync &sync) {
   using G = FftGeom<LOGN>;
   constexpr Sched S = G::S;
@@ -156,7 +157,7 @@ __device__ __forceinline__ void fft_pass(Load &load, Store &store, float2 *sm, c
     if constexpr (!FIRST) {
 #pragma unroll
       for (int r = 1; r < R; r++) {
-        float2 w = __ldg(&tw[TWO + (r - 1) * NS + k]);
+        float2 w = TW_SMEM ? tw[TWO + (r - 1) * NS + k] : __ldg(&tw[TWO + (r - 1) * NS + k]);
         if constexpr (INV) w.y = -w.y;
         v[q][r] = cmul(v[q][r], w);
       }
@@ -183,15 +184,17 @@ __device__ __forceinline__ void fft_pass(Load &load, Store &store, float2 *sm, c
 // last_pass_index<LOGN>(t, slot) gives the idx a given (t, slot) stores to.
 // `sm` needs FftGeom<LOGN>::SMEM float2 (unused for single-pass sizes N <= 16).
 // Only threads with t < T may call; all of them must (barriers inside).
-template <int LOGN, bool INV, bool LAST_INPLACE = false, bool FIRST_INPLACE = false, class Load, class Store,
-          class Sync>
-__device__ __forceinline__ void fft_run(Load load, Store store, float2 *sm, const float2 *__restrict__ tw, int t,
+// TW_SMEM: `tw` points to a copy of the pass-twiddle table in shared memory (plain loads) instead of
+// global memory (read-only path).
+template <int LOGN, bool INV, bool LAST_INPLACE = false, bool FIRST_INPLACE = false, bool TW_SMEM = false, class Load,
+          class Store, class Sync>
+__device__ __forceinline__ void fft_run(Load load, Store store, float2 *sm, const float2 *tw, int t,
                                         Sync sync) {
   constexpr Sched S = sched_for(LOGN);
-  fft_pass<LOGN, 0, INV, FIRST_INPLACE, LAST_INPLACE>(load, store, sm, tw, t, sync);
-  if constexpr (S.npass > 1) fft_pass<LOGN, 1, INV, FIRST_INPLACE, LAST_INPLACE>(load, store, sm, tw, t, sync);
-  if constexpr (S.npass > 2) fft_pass<LOGN, 2, INV, FIRST_INPLACE, LAST_INPLACE>(load, store, sm, tw, t, sync);
-  if constexpr (S.npass > 3) fft_pass<LOGN, 3, INV, FIRST_INPLACE, LAST_INPLACE>(load, store, sm, tw, t, sync);
+  fft_pass<LOGN, 0, INV, FIRST_INPLACE, LAST_INPLACE, TW_SMEM>(load, store, sm, tw, t, sync);
+  if constexpr (S.npass > 1) fft_pass<LOGN, 1, INV, FIRST_INPLACE, LAST_INPLACE, TW_SMEM>(load, store, sm, tw, t, sync);
+  if constexpr (S.npass > 2) fft_pass<LOGN, 2, INV, FIRST_INPLACE, LAST_INPLACE, TW_SMEM>(load, store, sm, tw, t, sync);
+  if constexpr (S.npass > 3) fft_pass<LOGN, 3, INV, FIRST_INPLACE, LAST_INPLACE, TW_SMEM>(load, store, sm, tw, t, sync);
 }
 
 // output index written by thread t's value `slot` in the last pass (same arithmetic as fft_pass)

@@ -163,3 +163,37 @@ def test_device_pointer_api_matches_host_api(eng):
     assert p.transform_dev(d2, d2, batch) == 0
     torch.cuda.synchronize()
     assert torch.equal(d2, d_in)
+
+
+@pytest.mark.parametrize("batch", [1, 5, 71, 300])
+def test_cluster_fft_every_transform_of_a_batch(eng, batch):
+    """The 65536-point real / 32768-point complex transforms run on 4-CTA clusters that exchange data through
+    distributed shared memory with fence-free barriers; a persistent cluster loops over several transforms
+    when batch > resident clusters. Check EVERY transform of the batch (a race shows up as a few wrong ones),
+    twice, and that the two runs agree bit for bit."""
+    size = 65536
+    rng = np.random.default_rng(batch)
+    x = rng.uniform(-1, 1, (batch, size)).astype(np.float32)
+    f = eng.Clrfft(0, size, True, max_batch=batch)
+    outs = []
+    for _ in range(2):
+        c = np.zeros((batch, size // 2), np.complex64)
+        assert f.transform(c.reshape(-1), x.reshape(-1).copy()) == 0
+        outs.append(c)
+    assert np.array_equal(outs[0], outs[1])
+    X = np.fft.rfft(x.astype(np.float64), axis=1)
+    want = 2 * X[:, : size // 2] / size
+    want[:, 0] = (X[:, 0].real + 1j * X[:, size // 2].real) / size
+    want[:, size // 4] = np.conj(want[:, size // 4])  # quirk Q3
+    err = np.linalg.norm(outs[0] - want, axis=1) / np.linalg.norm(want, axis=1)
+    assert err.max() < 2e-6, (int(err.argmax()), float(err.max()))
+    # complex path, forward and inverse, same kernel family
+    z = (rng.uniform(-1, 1, (batch, size // 2)) + 1j * rng.uniform(-1, 1, (batch, size // 2))).astype(np.complex64)
+    for fwd in (True, False):
+        p = eng.Clcfft(0, size // 2, fwd, max_batch=batch)
+        y = z.copy()
+        assert p.transform(y.reshape(-1)) == 0
+        zz = z.astype(np.complex128)
+        truth = np.fft.fft(zz, axis=1) / (size // 2) if fwd else np.fft.ifft(zz, axis=1) * (size // 2)
+        err = np.linalg.norm(y - truth, axis=1) / np.linalg.norm(truth, axis=1)
+        assert err.max() < 2e-6, (fwd, int(err.argmax()), float(err.max()))
