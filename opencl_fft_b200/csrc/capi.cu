@@ -149,10 +149,24 @@ static int launch_cfft_t(bool inv, const float2 *in, float2 *out, const float2 *
   return B2F_OK;
 }
 template <int LOGN>
-static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *w2, int batch,
-                         cudaStream_t st) {
+static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *w2, const float2 *hw,
+                         int batch, cudaStream_t st) {
   using B = BatchGeom<LOGN>;
   const int grid = (batch + B::TPB - 1) / B::TPB;
+  if constexpr (RegSplitGeom<LOGN>::OK) {
+    // register-level split / unsplit (fft_kernels.cuh, second half)
+    if (inv) {
+      int rc = set_smem(rfft_inv_reg_kernel<LOGN>, B::SMEM_BYTES);
+      if (rc) return rc;
+      rfft_inv_reg_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, hw, batch);
+    } else {
+      int rc = set_smem(rfft_fwd_reg_kernel<LOGN>, B::SMEM_BYTES);
+      if (rc) return rc;
+      rfft_fwd_reg_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, hw, batch, 1.0f / (float)(1 << LOGN));
+    }
+    CK(cudaGetLastError());
+    return B2F_OK;
+  }
   if (inv) {
     int rc = set_smem(rfft_inv_kernel<LOGN>, B::SMEM_BYTES);
     if (rc) return rc;
@@ -192,8 +206,8 @@ static int launch_cfft(int logn, bool inv, const float2 *in, float2 *out, const 
 #undef CALL
 }
 static int launch_rfft(int logn, bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *w2,
-                       int batch, cudaStream_t st) {
-#define CALL(L) launch_rfft_t<L>(inv, in, out, tw, w2, batch, st)
+                       const float2 *hw, int batch, cudaStream_t st) {
+#define CALL(L) launch_rfft_t<L>(inv, in, out, tw, w2, hw, batch, st)
   B2F_DISPATCH_LOGN(logn, CALL)
 #undef CALL
 }
@@ -376,6 +390,7 @@ struct FftPlanCore {
   int device = 0, N = 0, logn = 0, fwd = 1, max_batch = 1;
   float2 *d_tw = nullptr;   // pass twiddles (small path) or sub-plan twiddles (large path)
   float2 *d_w2 = nullptr;   // split twiddles (real plans)
+  float2 *d_hw = nullptr;   // folded split table 0.5*scale*i*w2 (forward) / its conjugate, unscaled (inverse)
   float2 *d_buf = nullptr;  // device buffer backing the host entry points
   LargePlan large;          // N > 2^kMaxSmemLogN
   cudaStream_t stream = nullptr;
@@ -395,7 +410,16 @@ struct FftPlanCore {
       if (rc) return rc;
     }
     if (real) {
-      rc = upload(make_split_twiddles(N), &d_w2);
+      std::vector<float2> w2 = make_split_twiddles(N), hw((size_t)N / 2 + 1);
+      rc = upload(w2, &d_w2);
+      if (rc) return rc;
+      const float s = fwd ? 1.0f / (float)N : 1.0f;  // powers of two: the folding is exact
+      for (int i = 0; i <= N / 2 && i < N; i++) {
+        // 0.5 * i * w2[i] = 0.5 * (-w.y, w.x); the inverse table is its conjugate (cl_fft.cpp:233-238 sign)
+        hw[i].x = -0.5f * s * w2[i].y;
+        hw[i].y = (fwd ? 0.5f : -0.5f) * s * w2[i].x;
+      }
+      rc = upload(hw, &d_hw);
       if (rc) return rc;
     }
     return B2F_OK;
@@ -408,6 +432,7 @@ struct FftPlanCore {
     cudaSetDevice(device);
     if (d_tw) cudaFree(d_tw);
     if (d_w2) cudaFree(d_w2);
+    if (d_hw) cudaFree(d_hw);
     if (d_buf) cudaFree(d_buf);
     large.destroy();
     if (stream) cudaStreamDestroy(stream);
@@ -421,7 +446,7 @@ struct FftPlanCore {
   }
   int run_real(const float2 *in, float2 *out, int batch, cudaStream_t st) {
     if (is_large()) return large.run_real(!fwd, in, out, d_w2, batch, st);
-    return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, batch, st);
+    return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, d_hw, batch, st);
   }
 };
 

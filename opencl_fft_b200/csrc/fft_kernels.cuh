@@ -120,4 +120,131 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
   fft_run<LOGN, true, false, true>(load, store, sm, tw, t, CtaSync());
 }
 
+
+// =====================================================================================================
+// Register-level real transforms for N >= 128 (schedules whose first and last passes leave every thread
+// with the 16 values X[t + m*T], m = 0..15, T = N/16). The pair partner of element (t, m) is element
+// (T - t, 15 - m) [(0, 16 - m) for t = 0], so the split / unsplit needs ONE partner thread: the two swap
+// half of their values through a small shared-memory staging area, each evaluates its 8 pairs once.
+// Against the generic kernels above this drops a full shared-memory round trip and halves the split
+// arithmetic: 0.5, the 1/N scaling and the quarter turn are folded into the table
+//   hw[i] = 0.5 * scale * i * w2[i]  (forward)      hw[i] = conj(0.5 * i * w2[i])  (inverse)
+// so that   out_i = hs*S + hw*D,  out_j = conj(hs*S - hw*D),  S = A + conj(B), D = conj(B) - A,
+// the same algebra as the reference's conv/iconv kernels (cl_fft.cpp:178-205), 12 instructions per pair.
+// =====================================================================================================
+template <bool INV>
+__device__ __forceinline__ void rfft_pair_folded(float2 &A, float2 &B, float2 hw, float hs) {
+  const float sx = A.x + B.x, sy = A.y - B.y;
+  const float dx = B.x - A.x, dy = -B.y - A.y;
+  const float px = hw.x * dx - hw.y * dy, py = hw.x * dy + hw.y * dx;
+  A = make_float2(fmaf(hs, sx, px), fmaf(hs, sy, py));
+  B = make_float2(fmaf(hs, sx, -px), fmaf(-hs, sy, py));
+}
+
+template <int LOGN>
+struct RegSplitGeom {
+  using G = FftGeom<LOGN>;
+  static constexpr Sched S = G::S;
+  static constexpr bool OK = (LOGN >= 7) && G::E == 16 && S.radix[S.npass - 1] == 16;
+  static constexpr int T = G::T;
+  static constexpr int R0 = S.radix[0];
+};
+
+// forward: in [batch][2N] float, out [batch][N] float2 (may alias). hw: folded table (scale included).
+template <int LOGN>
+__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
+    rfft_fwd_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
+                        int batch, float scale) {
+  using B = BatchGeom<LOGN>;
+  constexpr int N = 1 << LOGN, T = B::T;
+  extern __shared__ float2 smem[];
+  const int lt = threadIdx.x / T, t = threadIdx.x % T;
+  const long long b = (long long)blockIdx.x * B::TPB + lt;
+  const bool active = b < batch;
+  const float2 *src = in + (active ? b : 0) * N;
+  float2 *dst = out + (active ? b : 0) * N;
+  float2 *sm = smem + lt * FftGeom<LOGN>::SMEM;
+  float2 x[16];
+  auto load = [&](int idx, int) { return active ? __ldcs(src + idx) : make_float2(0.f, 0.f); };
+  auto store = [&](int, float2 v, int slot) { x[slot] = v; };  // last pass: slot == m, value X[t + m*T]
+  fft_run<LOGN, false>(load, store, sm, tw, t, CtaSync());
+  __syncthreads();  // every thread is past its last gather: sm becomes the staging area [8][T]
+#pragma unroll
+  for (int m = 8; m < 16; m++) sm[(m - 8) * T + t] = x[m];
+  __syncthreads();
+  if (!active) return;
+  const int pt = (t == 0) ? 0 : T - t;  // partner thread (itself for t = 0 and t = T/2)
+  const float hs = 0.5f * scale;
+#pragma unroll
+  for (int m = 0; m < 8; m++) {
+    if (m == 0 && t == 0) {
+      dst[0] = make_float2((x[0].x + x[0].y) * hs, (x[0].x - x[0].y) * hs);   // packed (DC, Nyquist)
+      dst[N / 2] = make_float2(x[8].x * scale, x[8].y * scale);               // never visited by the reference (Q3)
+      continue;
+    }
+    const int pm = (t == 0) ? 16 - m : 15 - m;
+    float2 a = x[m], bb = sm[(pm - 8) * T + pt];
+    rfft_pair_folded<false>(a, bb, __ldg(&hw[t + m * T]), hs);
+    __stcs(dst + t + m * T, a);
+    __stcs(dst + pt + pm * T, bb);
+  }
+}
+
+// inverse: in [batch][N] float2, out [batch][2N] float (may alias). hw: folded inverse table.
+template <int LOGN>
+__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
+    rfft_inv_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
+                        int batch) {
+  using B = BatchGeom<LOGN>;
+  using RS = RegSplitGeom<LOGN>;
+  constexpr int N = 1 << LOGN, T = B::T, R0 = RS::R0;
+  extern __shared__ float2 smem[];
+  const int lt = threadIdx.x / T, t = threadIdx.x % T;
+  const long long b = (long long)blockIdx.x * B::TPB + lt;
+  const bool active = b < batch;
+  const float2 *src = in + (active ? b : 0) * N;
+  float2 *dst = out + (active ? b : 0) * N;
+  float2 *sm = smem + lt * FftGeom<LOGN>::SMEM;
+  float2 x[16];
+#pragma unroll
+  for (int m = 0; m < 16; m++) x[m] = active ? __ldcs(src + t + m * T) : make_float2(0.f, 0.f);
+  const int pt = (t == 0) ? 0 : T - t;
+  // exchange 1: my upper half to the partner
+#pragma unroll
+  for (int m = 8; m < 16; m++) sm[(m - 8) * T + t] = x[m];
+  __syncthreads();
+  float2 hi[8];  // unsplit high members, owned by the partner thread
+#pragma unroll
+  for (int m = 0; m < 8; m++) {
+    const int pm = (t == 0) ? 16 - m : 15 - m;
+    if (m == 0 && t == 0) {
+      x[0] = make_float2(x[0].x + x[0].y, x[0].x - x[0].y);
+      hi[0] = x[8];  // element N/2 passes through (it is this thread's own slot 8)
+      continue;
+    }
+    float2 a = x[m], bb = sm[(pm - 8) * T + pt];
+    rfft_pair_folded<true>(a, bb, __ldg(&hw[t + m * T]), 0.5f);
+    x[m] = a;
+    hi[m] = bb;
+  }
+  __syncthreads();
+  // exchange 2: hand the high members back to their owners
+#pragma unroll
+  for (int m = 0; m < 8; m++) {
+    const int pm = (t == 0) ? ((16 - m) & 15) : 15 - m;  // (t = 0, m = 0) parks element N/2 in slot 8
+    const int slot = (t == 0 && m == 0) ? 8 : pm;
+    sm[(slot - 8) * T + pt] = hi[m];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 8; m < 16; m++) x[m] = sm[(m - 8) * T + t];
+  __syncthreads();  // staging is the engine's work buffer from here on
+  // first pass: value index m of (idx, slot): idx = (t + q*T) + r*(N/R0), slot = q*R0 + r  ->  m = q + r*(16/R0)
+  auto load = [&](int, int slot) { return x[(slot / R0) + (slot % R0) * (16 / R0)]; };
+  auto store = [&](int idx, float2 v, int) {
+    if (active) __stcs(dst + idx, v);
+  };
+  fft_run<LOGN, true>(load, store, sm, tw, t, CtaSync());
+}
+
 }  // namespace b2f
