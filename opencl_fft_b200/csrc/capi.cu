@@ -213,6 +213,73 @@ static int launch_rfft(int logn, bool inv, const float2 *in, float2 *out, const 
 }
 
 
+// ---- cluster plan (fft_cluster.cuh): N = N1 * 16 on persistent 4-CTA clusters -------------------------------
+struct ClusterPlan {
+  int logn = 0, log1 = 0, max_clusters = 0;
+  float2 *d_ctw1 = nullptr, *d_ctwl = nullptr;  // N1-point pass twiddles, [16][N1] inter-step table
+  bool ok() const { return d_ctwl != nullptr; }
+  static bool wanted(int logn) {
+    if (getenv("B2F_NO_CLUSTER_FFT")) return false;
+    const char *lo = getenv("B2F_CLUSTER_FFT_MIN_LOGN");
+    const int min_logn = lo ? atoi(lo) : 15;
+    return logn >= min_logn && logn >= 13 && logn <= 15;
+  }
+  int init(int logn_) {
+    logn = logn_;
+    log1 = logn - 4;
+    const int N = 1 << logn, CN1 = 1 << log1;
+    int rc;
+    if ((rc = upload(make_pass_twiddles(log1), &d_ctw1))) return rc;
+    std::vector<float2> t((size_t)N);
+    for (int k1 = 0; k1 < CN1; k1++)
+      for (int n2 = 0; n2 < 16; n2++) t[(size_t)n2 * CN1 + k1] = ref_twiddle((long long)n2 * k1, N);
+    return upload(t, &d_ctwl);
+  }
+  void destroy() {
+    if (d_ctw1) cudaFree(d_ctw1);
+    if (d_ctwl) cudaFree(d_ctwl);
+    d_ctw1 = d_ctwl = nullptr;
+  }
+  // one persistent 4-CTA cluster per 4 SMs, looping over the batch
+  template <int L1, bool INV, bool REAL>
+  int run_cluster_t(const float2 *in, float2 *out, const float2 *w2, int batch, float scale, cudaStream_t st) {
+    using C = ClusterGeom<L1>;
+    auto kern = fft_cluster_kernel<L1, INV, REAL>;
+    int rc = set_smem(kern, C::SMEM_BYTES);
+    if (rc) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(C::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters == 0) {
+      cfg.gridDim = dim3(C::S * 64, 1, 1);
+      int n = 0;
+      CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      max_clusters = n > 0 ? n : 1;
+    }
+    const int ncl = batch < max_clusters ? batch : max_clusters;
+    cfg.gridDim = dim3(C::S * ncl, 1, 1);
+    CK(cudaLaunchKernelEx(&cfg, kern, in, out, (const float2 *)d_ctw1, (const float2 *)d_ctwl, w2, batch, scale));
+    return B2F_OK;
+  }
+  template <bool INV, bool REAL>
+  int run(const float2 *in, float2 *out, const float2 *w2, int batch, float scale, cudaStream_t st) {
+    switch (log1) {
+      case 9: return run_cluster_t<9, INV, REAL>(in, out, w2, batch, scale, st);
+      case 10: return run_cluster_t<10, INV, REAL>(in, out, w2, batch, scale, st);
+      case 11: return run_cluster_t<11, INV, REAL>(in, out, w2, batch, scale, st);
+      default: return B2F_ERR_UNSUPPORTED;
+    }
+  }
+};
+
 // ---- four-step plan for N > 2^kMaxSmemLogN ----------------------------------------------------------------
 struct LargePlan {
   int logn = 0, log1 = 0, log2 = 0, chunk = 1;
@@ -220,8 +287,13 @@ struct LargePlan {
   // cluster path (fft_cluster.cuh): N = N1 * 16, N1-point pass twiddles and the [N1][16] inter-step table
   float2 *d_ctw1 = nullptr, *d_ctwl = nullptr;
   int cluster_log1 = 0, max_clusters = 0;
-  // transforms per chunk: the scratch matrix of a chunk should stay in the 126 MB L2 between the two steps
-  static constexpr size_t kScratchBytes = 32u << 20;
+  // Scratch matrix between the two steps. Measured on B200 (1024 x 65536-point and 2048 x 32768-point batches):
+  // cutting the batch into L2-sized chunks (32 MB: 2.3 TB/s), pipelining the chunks over two streams (2.3 TB/s)
+  // and a single persistent kernel with ticketed column/row items and an L2-resident double buffer (2.4 TB/s)
+  // are all SLOWER than two long launches whose scratch simply goes through HBM (2.9 TB/s): short launches
+  // run as one wave of CTAs in phase lockstep, long ones desynchronise and overlap loads, butterflies and
+  // stores. So the scratch covers the whole batch, up to 1 GiB.
+  static constexpr size_t kScratchBytes = 1u << 30;
   int init(int logn_, int max_batch) {
     logn = logn_;
     log1 = logn / 2;
@@ -393,6 +465,7 @@ struct FftPlanCore {
   float2 *d_hw = nullptr;   // folded split table 0.5*scale*i*w2 (forward) / its conjugate, unscaled (inverse)
   float2 *d_buf = nullptr;  // device buffer backing the host entry points
   LargePlan large;          // N > 2^kMaxSmemLogN
+  ClusterPlan cluster;      // N = 2^13..2^15 on thread-block clusters (when selected)
   cudaStream_t stream = nullptr;
   Staging sg_in, sg_out;
   bool is_large() const { return logn > kMaxSmemLogN; }
@@ -402,6 +475,10 @@ struct FftPlanCore {
     int rc = check_device(dev);
     if (rc) return rc;
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (ClusterPlan::wanted(logn)) {
+      rc = cluster.init(logn);
+      if (rc) return rc;
+    }
     if (is_large()) {
       rc = large.init(logn, max_batch);
       if (rc) return rc;
@@ -435,16 +512,24 @@ struct FftPlanCore {
     if (d_hw) cudaFree(d_hw);
     if (d_buf) cudaFree(d_buf);
     large.destroy();
+    cluster.destroy();
     if (stream) cudaStreamDestroy(stream);
     sg_in.release();
     sg_out.release();
   }
   int run_c2c(const float2 *in, float2 *out, int batch, cudaStream_t st) {
     const float scale = fwd ? 1.0f / (float)N : 1.0f;
+    // complex transforms: the two-kernel four-step path measures faster than the cluster kernel (2.98 vs
+    // 2.05 TB/s at N = 32768); the cluster kernel earns its keep on the real forward transform, where it also
+    // absorbs the split pass. B2F_CLUSTER_C2C=1 forces it for experiments.
+    if (cluster.ok() && (!is_large() || getenv("B2F_CLUSTER_C2C")))
+      return fwd ? cluster.run<false, false>(in, out, nullptr, batch, scale, st)
+                 : cluster.run<true, false>(in, out, nullptr, batch, scale, st);
     if (is_large()) return large.run_c2c(!fwd, in, out, batch, scale, st);
     return launch_cfft(logn, !fwd, in, out, d_tw, batch, scale, st);
   }
   int run_real(const float2 *in, float2 *out, int batch, cudaStream_t st) {
+    if (cluster.ok() && fwd) return cluster.run<false, true>(in, out, d_w2, batch, 1.0f / (float)N, st);
     if (is_large()) return large.run_real(!fwd, in, out, d_w2, batch, st);
     return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, d_hw, batch, st);
   }

@@ -36,7 +36,7 @@ struct ClusterGeom {
   static constexpr int THREADS = COLS * T1;        // == N1 / 4 == rows owned by a CTA
   static constexpr int COLSTRIDE = G1::SMEM + 3;   // float2 per column region; == 4 (mod 16): the
                                                    // columns a half-warp touches land on distinct banks
-  static constexpr int CTAS_PER_SM = (CLUSTER == 4) ? 2 : 1;
+  static constexpr int CTAS_PER_SM = (CLUSTER == 4) ? 1024 / THREADS : 1;  // caps registers at 64 per thread
   static constexpr int TW_ENTRIES = sched_tw_total(G1::S) + 1;  // pass twiddles kept in shared memory
   static constexpr int SMEM_BYTES = (COLS * COLSTRIDE + TW_ENTRIES) * (int)sizeof(float2);
   static_assert(THREADS == N1 / S, "one row per thread in step 3");

@@ -237,4 +237,16 @@ __device__ __forceinline__ float2 rfft_dc(float2 c0) {
   return INV ? make_float2(c0.x + c0.y, c0.x - c0.y) : make_float2((c0.x + c0.y) * .5f, (c0.x - c0.y) * .5f);
 }
 
+// the same pair with 0.5, the scaling and the quarter turn folded into the table entry hw = 0.5*scale*i*w
+// (forward) or its conjugate (inverse) and hs = 0.5*scale: out_i = hs*S + hw*D, out_j = conj(hs*S - hw*D) with
+// S = A + conj(B), D = conj(B) - A. 12 instructions per pair.
+template <bool INV>
+__device__ __forceinline__ void rfft_pair_folded(float2 &A, float2 &B, float2 hw, float hs) {
+  const float sx = A.x + B.x, sy = A.y - B.y;
+  const float dx = B.x - A.x, dy = -B.y - A.y;
+  const float px = hw.x * dx - hw.y * dy, py = hw.x * dy + hw.y * dx;
+  A = make_float2(fmaf(hs, sx, px), fmaf(hs, sy, py));
+  B = make_float2(fmaf(hs, sx, -px), fmaf(-hs, sy, py));
+}
+
 }  // namespace b2f

@@ -21,13 +21,14 @@ struct BatchGeom {
   static constexpr int TPB = (T >= kTargetThreads) ? 1 : (kTargetThreads / T);  // transforms per CTA
   static constexpr int THREADS = T * TPB;
   static constexpr int SMEM_BYTES = TPB * G::SMEM * (int)sizeof(float2);
+  static constexpr int MIN_BLOCKS = 1024 / THREADS;  // caps registers at 64/thread: 32 resident warps per SM
 };
 
 // ---- complex to complex ------------------------------------------------------------------------
 // in/out: [batch][N] float2, may alias (each CTA gathers its whole transform before it scatters).
 // scale: 1/N for the reference's forward transform (cl_fft.cpp:39-40), 1 for the inverse.
 template <int LOGN, bool INV>
-__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
+__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
     cfft_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, int batch, float scale) {
   using B = BatchGeom<LOGN>;
   constexpr int N = 1 << LOGN;
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
 // Output convention of the reference: element 0 = (DC, Nyquist)/size packed, element k =
 // 2 X[k]/size, element N/2 left as the plain FFT value (the reference's split never visits it, Q3).
 template <int LOGN>
-__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
+__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
     rfft_fwd_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ w2,
                     int batch) {
   using B = BatchGeom<LOGN>;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
 // ---- complex to real (inverse) -------------------------------------------------------------------
 // in: [batch][N] float2 in the layout rfft_fwd_kernel writes, out: [batch][2N] float, may alias.
 template <int LOGN>
-__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
+__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
     rfft_inv_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ w2,
                     int batch) {
   using B = BatchGeom<LOGN>;
@@ -132,15 +133,6 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
 // so that   out_i = hs*S + hw*D,  out_j = conj(hs*S - hw*D),  S = A + conj(B), D = conj(B) - A,
 // the same algebra as the reference's conv/iconv kernels (cl_fft.cpp:178-205), 12 instructions per pair.
 // =====================================================================================================
-template <bool INV>
-__device__ __forceinline__ void rfft_pair_folded(float2 &A, float2 &B, float2 hw, float hs) {
-  const float sx = A.x + B.x, sy = A.y - B.y;
-  const float dx = B.x - A.x, dy = -B.y - A.y;
-  const float px = hw.x * dx - hw.y * dy, py = hw.x * dy + hw.y * dx;
-  A = make_float2(fmaf(hs, sx, px), fmaf(hs, sy, py));
-  B = make_float2(fmaf(hs, sx, -px), fmaf(-hs, sy, py));
-}
-
 template <int LOGN>
 struct RegSplitGeom {
   using G = FftGeom<LOGN>;
@@ -152,7 +144,7 @@ struct RegSplitGeom {
 
 // forward: in [batch][2N] float, out [batch][N] float2 (may alias). hw: folded table (scale included).
 template <int LOGN>
-__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
+__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
     rfft_fwd_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
                         int batch, float scale) {
   using B = BatchGeom<LOGN>;
@@ -192,7 +184,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
 
 // inverse: in [batch][N] float2, out [batch][2N] float (may alias). hw: folded inverse table.
 template <int LOGN>
-__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS)
+__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
     rfft_inv_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
                         int batch) {
   using B = BatchGeom<LOGN>;
