@@ -283,10 +283,7 @@ struct ClusterPlan {
 // ---- four-step plan for N > 2^kMaxSmemLogN ----------------------------------------------------------------
 struct LargePlan {
   int logn = 0, log1 = 0, log2 = 0, chunk = 1;
-  float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twl = nullptr, *d_scratch = nullptr;
-  // cluster path (fft_cluster.cuh): N = N1 * 16, N1-point pass twiddles and the [N1][16] inter-step table
-  float2 *d_ctw1 = nullptr, *d_ctwl = nullptr;
-  int cluster_log1 = 0, max_clusters = 0;
+  float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twl = nullptr, *d_scratch = nullptr, *d_scratch_base = nullptr;
   // Scratch matrix between the two steps. Measured on B200 (1024 x 65536-point and 2048 x 32768-point batches):
   // cutting the batch into L2-sized chunks (32 MB: 2.3 TB/s), pipelining the chunks over two streams (2.3 TB/s)
   // and a single persistent kernel with ticketed column/row items and an L2-resident double buffer (2.4 TB/s)
@@ -310,52 +307,13 @@ struct LargePlan {
     if (chunk < 1) chunk = 1;
     if (chunk > max_batch) chunk = max_batch < 1 ? 1 : max_batch;
     CK(cudaMalloc((void **)&d_scratch, (size_t)chunk * N * sizeof(float2)));
-    if (logn == 15 && !getenv("B2F_NO_CLUSTER_FFT")) {
-      cluster_log1 = logn - 4;
-      const int CN1 = 1 << cluster_log1;
-      if ((rc = upload(make_pass_twiddles(cluster_log1), &d_ctw1))) return rc;
-      std::vector<float2> t((size_t)N);
-      for (int k1 = 0; k1 < CN1; k1++)
-        for (int n2 = 0; n2 < 16; n2++) t[(size_t)n2 * CN1 + k1] = ref_twiddle((long long)n2 * k1, N);
-      if ((rc = upload(t, &d_ctwl))) return rc;
-    }
     return B2F_OK;
   }
   void destroy() {
-    for (void *p : {(void *)d_tw1, (void *)d_tw2, (void *)d_twl, (void *)d_scratch, (void *)d_ctw1, (void *)d_ctwl})
+    for (void *p : {(void *)d_tw1, (void *)d_tw2, (void *)d_twl, (void *)d_scratch})
       if (p) cudaFree(p);
-    d_tw1 = d_tw2 = d_twl = d_scratch = d_ctw1 = d_ctwl = nullptr;
+    d_tw1 = d_tw2 = d_twl = d_scratch = nullptr;
   }
-  // one persistent 4-CTA cluster per 4 SMs, looping over the batch
-  template <int L1, bool INV, bool REAL>
-  int run_cluster_t(const float2 *in, float2 *out, const float2 *w2, int batch, float scale, cudaStream_t st) {
-    using C = ClusterGeom<L1>;
-    auto kern = fft_cluster_kernel<L1, INV, REAL>;
-    int rc = set_smem(kern, C::SMEM_BYTES);
-    if (rc) return rc;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(C::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = C::S;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (max_clusters == 0) {
-      cfg.gridDim = dim3(C::S * 64, 1, 1);
-      int n = 0;
-      CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-      max_clusters = n > 0 ? n : 1;
-    }
-    const int ncl = batch < max_clusters ? batch : max_clusters;
-    cfg.gridDim = dim3(C::S * ncl, 1, 1);
-    CK(cudaLaunchKernelEx(&cfg, kern, in, out, (const float2 *)d_ctw1, (const float2 *)d_ctwl, w2, batch, scale));
-    return B2F_OK;
-  }
-  bool has_cluster() const { return d_ctwl != nullptr; }
   template <int L1, int L2, bool INV>
   int run_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st) {
     using L = LargeGeom<L1, L2>;
@@ -378,9 +336,6 @@ struct LargePlan {
     return B2F_OK;
   }
   int run_c2c(bool inv, const float2 *in, float2 *out, int batch, float scale, cudaStream_t st) {
-    if (has_cluster() && cluster_log1 == 11)
-      return inv ? run_cluster_t<11, true, false>(in, out, nullptr, batch, scale, st)
-                 : run_cluster_t<11, false, false>(in, out, nullptr, batch, scale, st);
     if (logn == 15) return inv ? run_t<7, 8, true>(in, out, batch, scale, st) : run_t<7, 8, false>(in, out, batch, scale, st);
     if (logn == 16) return inv ? run_t<8, 8, true>(in, out, batch, scale, st) : run_t<8, 8, false>(in, out, batch, scale, st);
     return B2F_ERR_UNSUPPORTED;
@@ -390,8 +345,6 @@ struct LargePlan {
     const long long pairs = (long long)batch * (N / 2);
     const int grid = (int)((pairs + 255) / 256);
     int rc;
-    if (!inv && has_cluster() && cluster_log1 == 11)
-      return run_cluster_t<11, false, true>(in, out, w2, batch, 1.0f / (float)N, st);
     if (!inv) {
       if ((rc = run_c2c(false, in, out, batch, 1.0f / (float)N, st))) return rc;
       rfft_split_kernel<false><<<grid, 256, 0, st>>>(out, out, w2, N, pairs);
@@ -475,15 +428,15 @@ struct FftPlanCore {
     int rc = check_device(dev);
     if (rc) return rc;
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    if (ClusterPlan::wanted(logn)) {
-      rc = cluster.init(logn);
-      if (rc) return rc;
-    }
     if (is_large()) {
       rc = large.init(logn, max_batch);
       if (rc) return rc;
     } else {
       rc = upload(make_pass_twiddles(logn), &d_tw);
+      if (rc) return rc;
+    }
+    if (ClusterPlan::wanted(logn)) {
+      rc = cluster.init(logn);
       if (rc) return rc;
     }
     if (real) {
