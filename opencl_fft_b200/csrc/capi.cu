@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -833,13 +834,14 @@ struct b2f_dconv {
   int wp = 0;  // the reference's ring position (cl_dconv.cpp:124), kept for the coefficient ring
   int cur = 0; // which history buffer is current
   float *d_hist[2] = {nullptr, nullptr};
-  float *d_coefs = nullptr, *d_in1 = nullptr, *d_in2 = nullptr, *d_out = nullptr;
+  float *d_coefs = nullptr, *d_grev = nullptr, *d_in1 = nullptr, *d_in2 = nullptr, *d_out = nullptr;
   cudaStream_t stream = nullptr;
   Staging sg_in, sg_in2, sg_out;
   int L() const { return irsize + vsize; }
   void destroy() {
     cudaSetDevice(device);
-    for (void *p : {(void *)d_hist[0], (void *)d_hist[1], (void *)d_coefs, (void *)d_in1, (void *)d_in2, (void *)d_out})
+    for (void *p : {(void *)d_hist[0], (void *)d_hist[1], (void *)d_coefs, (void *)d_grev, (void *)d_in1, (void *)d_in2,
+                    (void *)d_out})
       if (p) cudaFree(p);
     if (stream) cudaStreamDestroy(stream);
     sg_in.release();
@@ -873,6 +875,8 @@ extern "C" int b2f_dconv_create(b2f_dconv **out, int device, int irsize, int vsi
   }
   if ((e = cudaMalloc((void **)&h->d_coefs, cb)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc coefs"));
   if ((e = cudaMemsetAsync(h->d_coefs, 0, cb, h->stream)) != cudaSuccess) return fail(cuda_fail(e, "memset"));
+  if ((e = cudaMalloc((void **)&h->d_grev, hb)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc grev"));
+  if ((e = cudaMemsetAsync(h->d_grev, 0, hb, h->stream)) != cudaSuccess) return fail(cuda_fail(e, "memset"));
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(cuda_fail(e, "sync"));
   *out = h;
   return B2F_OK;
@@ -891,37 +895,41 @@ extern "C" int b2f_dconv_reset(b2f_dconv *h) {
   h->wp = 0;
   return B2F_OK;
 }
+// keep the reversed tap copy the FIR kernel streams in step with the coefficient ring
+static int dconv_reverse(b2f_dconv *h, cudaStream_t st) {
+  dim3 grid((h->irsize + 255) / 256, h->channels, 1);
+  dconv_reverse_kernel<<<grid, 256, 0, st>>>(h->d_grev, h->d_coefs, h->irsize, h->L());
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
 extern "C" int b2f_dconv_push_ir_dev(b2f_dconv *h, const void *d_ir, size_t ir_stride, void *stream) {
   if (!h || !d_ir || ir_stride < (size_t)h->irsize) return B2F_ERR_INVALID_VALUE;
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpy2DAsync(h->d_coefs, (size_t)h->L() * sizeof(float), d_ir, ir_stride * sizeof(float),
                        (size_t)h->irsize * sizeof(float), h->channels, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  return B2F_OK;
+  return dconv_reverse(h, (cudaStream_t)stream);
 }
 extern "C" int b2f_dconv_push_ir_host(b2f_dconv *h, const float *ir, size_t ir_stride) {
   if (!h || !ir || ir_stride < (size_t)h->irsize) return B2F_ERR_INVALID_VALUE;
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpy2DAsync(h->d_coefs, (size_t)h->L() * sizeof(float), ir, ir_stride * sizeof(float),
                        (size_t)h->irsize * sizeof(float), h->channels, cudaMemcpyHostToDevice, h->stream));
+  int rc = dconv_reverse(h, h->stream);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return B2F_OK;
 }
 
-static bool tiles_too_many(long long nout) { return (nout + kDcTileOut - 1) / kDcTileOut > 65535; }
-static int dconv_enqueue(b2f_dconv *h, float *d_out, const float *d_in, int nblocks, cudaStream_t st) {
-  DconvArgs a;
-  a.hist_in = h->d_hist[h->cur];
-  a.hist_out = h->d_hist[h->cur ^ 1];
-  a.coefs = h->d_coefs;
-  a.in = d_in, a.out = d_out;
-  a.irsize = h->irsize, a.vsize = h->vsize, a.nout = nblocks * h->vsize;
-  a.coef_stride = h->L();
-  const int tiles = (a.nout + kDcTileOut - 1) / kDcTileOut;
+static bool tiles_too_many(long long nout) { return (nout + 255) / 256 > 65535; }
+template <int TN>
+static int dconv_launch_t(const DconvArgs &a, int channels, cudaStream_t st) {
+  using G = DconvGeom<TN>;
+  const int tiles = (a.nout + G::TILE - 1) / G::TILE;
   // split the taps over a cluster when the grid would not cover the GPU
   int S = 1;
-  while (S < 8 && (long long)tiles * h->channels * S < 296 && h->irsize / (S * 2) >= 64) S *= 2;
+  while (S < 8 && (long long)tiles * channels * S < 296 && a.irsize / (S * 2) >= 64) S *= 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(S, tiles, h->channels);
+  cfg.gridDim = dim3(S, tiles, channels);
   cfg.blockDim = dim3(kDcThreads, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
@@ -932,7 +940,20 @@ static int dconv_enqueue(b2f_dconv *h, float *d_out, const float *d_in, int nblo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, dconv_fir_kernel, a));
+  CK(cudaLaunchKernelEx(&cfg, dconv_fir_kernel<TN>, a));
+  return B2F_OK;
+}
+static int dconv_enqueue(b2f_dconv *h, float *d_out, const float *d_in, int nblocks, cudaStream_t st) {
+  DconvArgs a;
+  a.hist_in = h->d_hist[h->cur];
+  a.hist_out = h->d_hist[h->cur ^ 1];
+  a.grev = h->d_grev;
+  a.in = d_in, a.out = d_out;
+  a.irsize = h->irsize, a.nout = nblocks * h->vsize;
+  a.vec_ok = (h->irsize % 4 == 0) && (a.nout % 4 == 0) && ((uintptr_t)d_in % 16 == 0);
+  // 16 outputs per thread when there is enough stream per launch to fill 512-output tiles, 8 otherwise
+  int rc = a.nout >= 512 ? dconv_launch_t<16>(a, h->channels, st) : dconv_launch_t<8>(a, h->channels, st);
+  if (rc) return rc;
   h->cur ^= 1;
   h->wp = (int)(((long long)h->wp + (long long)nblocks * h->vsize) % h->L());  // cl_dconv.cpp:124
   return B2F_OK;
@@ -945,7 +966,7 @@ extern "C" int b2f_dconv_process_dev(b2f_dconv *h, void *d_out, const void *d_in
 }
 static int dconv_coef_write(b2f_dconv *h, const float *d_in2, cudaStream_t st) {
   dim3 grid((h->vsize + 255) / 256, h->channels, 1);
-  dconv_coef_write_kernel<<<grid, 256, 0, st>>>(h->d_coefs, d_in2, h->vsize, h->L(), h->wp);
+  dconv_coef_write_kernel<<<grid, 256, 0, st>>>(h->d_coefs, h->d_grev, d_in2, h->vsize, h->irsize, h->L(), h->wp);
   CK(cudaGetLastError());
   return B2F_OK;
 }

@@ -2,19 +2,20 @@
 //
 // Replaces cl_conv::Cldconv::convolution (cl_dconv.cpp:109-132) and its `convol` kernel (32-43):
 // irsize*vsize work-items, each doing ONE multiply and a CAS-loop float atomic add into out[n]
-// (4096-way contention per output at the BASELINE shape). Here every thread keeps 8 outputs in
-// registers and slides over the taps, 64 FMAs per 4 shared-memory vector loads; partial sums meet
-// once through shared memory (and, when the taps are split over a thread-block cluster, once
-// through distributed shared memory). No atomics, deterministic.
+// (4096-way contention per output at the BASELINE shape). Here every thread keeps TN (8 or 16) outputs
+// in registers and slides over the taps: TN*8 FMAs per 8-tap step against 4 shared-memory vector loads;
+// partial sums meet once through shared memory (and, when the taps are split over a thread-block
+// cluster, once through distributed shared memory). No atomics, deterministic.
 //
 // Semantics: with xl = [last irsize samples of the stream | the new samples],
-//   out[t] = sum_{h < irsize} xl[t + h] * coefs[irsize-1-h]      (== sum_c ir[c] x[t-1-c], Q9)
+//   out[t] = sum_{h < irsize} xl[t + h] * g[h],   g[h] = coefs[irsize-1-h]      (== sum_c ir[c] x[t-1-c], Q9)
 // which is what the reference's ring arithmetic del[(wp+n+h) mod L] evaluates to whenever its ring
 // write is valid (irsize % vsize == 0), extended to any number of consecutive blocks per launch.
 //
 // Layout: hist [channels][irsize] float (double-buffered), coefs [channels][irsize+vsize] float (the
 // reference's coefficient ring, same positions, so the time-varying variant re-records taps exactly
-// as cl_dconv.cpp:134-148 does), in/out [channels][nblocks*vsize].
+// as cl_dconv.cpp:134-148 does), grev [channels][irsize] float = the reversed taps g the kernel streams,
+// in/out [channels][nblocks*vsize].
 #pragma once
 
 #include <cooperative_groups.h>
@@ -26,27 +27,39 @@ namespace cg = cooperative_groups;
 
 constexpr int kDcWarps = 8;                    // warps per CTA; each takes a slice of the tap chunk
 constexpr int kDcThreads = kDcWarps * 32;
-constexpr int kDcTN = 8;                       // outputs per thread
-constexpr int kDcTileOut = 32 * kDcTN;         // outputs per CTA tile (every warp covers all of them)
 constexpr int kDcKC = 1024;                    // taps staged per chunk
 constexpr int kDcWarpTaps = kDcKC / kDcWarps;  // taps per warp per chunk (multiple of 8)
-constexpr int kDcXs = kDcTileOut + kDcKC;      // staged input window
+
+template <int TN>
+struct DconvGeom {
+  static constexpr int TILE = 32 * TN;       // outputs per CTA tile (every warp covers all of them)
+  static constexpr int XS = TILE + kDcKC;    // staged input window (logical floats)
+  // Shared-memory index of logical float i: 4 pad floats after every TN. A lane owns TN consecutive
+  // outputs, so its 128-bit window loads start TN floats from its neighbour's; unpadded that is a 4-way
+  // (TN=16) / 2-way (TN=8) bank conflict and the kernel becomes shared-memory bound (measured: 50 instead
+  // of 45 TFLOP/s was all TN=16 bought). With the pad the 8 lanes of a quarter-warp hit 8 distinct
+  // 16-byte bank groups.
+  static constexpr int XS_PADDED = XS + 4 * (XS / TN) + 4;
+  __host__ __device__ static constexpr int xi(int i) { return i + 4 * (i / TN); }
+};
 
 struct DconvArgs {
   const float *hist_in;  // [channels][irsize]
   float *hist_out;       // [channels][irsize]  (other half of the double buffer)
-  const float *coefs;    // [channels][irsize + vsize]
+  const float *grev;     // [channels][irsize]  reversed taps
   const float *in;       // [channels][nout]
   float *out;            // [channels][nout]
-  int irsize, vsize, nout;
-  int coef_stride;       // irsize + vsize
+  int irsize, nout;
+  int vec_ok;            // irsize % 4 == 0 && nout % 4 == 0: 128-bit staging loads are aligned
 };
 
 // grid = (S, tiles, channels), cluster = (S,1,1): rank r takes taps [r*irsize/S, (r+1)*irsize/S) (rounded to 8).
+template <int TN>
 __global__ void __launch_bounds__(kDcThreads) dconv_fir_kernel(DconvArgs a) {
-  __shared__ __align__(16) float xs[kDcXs];
+  using G = DconvGeom<TN>;
+  __shared__ __align__(16) float xs[G::XS_PADDED];
   __shared__ __align__(16) float gs[kDcKC];
-  __shared__ __align__(16) float red[kDcWarps][kDcTileOut];
+  __shared__ __align__(16) float red[kDcWarps][G::TILE];
 
   cg::cluster_group cluster = cg::this_cluster();
   const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
@@ -55,72 +68,105 @@ __global__ void __launch_bounds__(kDcThreads) dconv_fir_kernel(DconvArgs a) {
   const int irsize = a.irsize, nout = a.nout;
   const float *hist = a.hist_in + (size_t)ch * irsize;
   const float *in = a.in + (size_t)ch * nout;
-  const float *coefs = a.coefs + (size_t)ch * a.coef_stride;
-  const int t0 = tile * kDcTileOut;
+  const float *grev = a.grev + (size_t)ch * irsize;
+  const int t0 = tile * G::TILE;
   const int total = irsize + nout;  // length of xl
 
-  int k_lo = (int)((long long)rank * irsize / S) & ~7;
-  int k_hi = (rank == S - 1) ? irsize : ((int)((long long)(rank + 1) * irsize / S) & ~7);
+  const int k_lo = (int)((long long)rank * irsize / S) & ~7;
+  const int k_hi = (rank == S - 1) ? irsize : ((int)((long long)(rank + 1) * irsize / S) & ~7);
 
-  float acc[kDcTN];
+  float acc[TN];
 #pragma unroll
-  for (int i = 0; i < kDcTN; i++) acc[i] = 0.f;
+  for (int i = 0; i < TN; i++) acc[i] = 0.f;
 
   for (int k0 = k_lo; k0 < k_hi; k0 += kDcKC) {
-    // stage xl[t0 + k0, +kDcXs) and the reversed taps g[k0, +kDcKC)
-    for (int i = tid; i < kDcXs; i += kDcThreads) {
-      const int xi = t0 + k0 + i;
-      float v = 0.f;
-      if (xi < total) v = xi < irsize ? hist[xi] : in[xi - irsize];
-      xs[i] = v;
-    }
-    for (int i = tid; i < kDcKC; i += kDcThreads) {
-      const int k = k0 + i;
-      gs[i] = k < k_hi ? coefs[irsize - 1 - k] : 0.f;
+    // ---- stage xl[t0 + k0, +XS) and g[k0, +KC) -------------------------------------------------------
+    if (a.vec_ok) {
+      for (int i = tid * 4; i < G::XS; i += kDcThreads * 4) {
+        const int xi = t0 + k0 + i;  // multiple of 4; irsize % 4 == 0, so a float4 never straddles the seam
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xi < total) v = xi < irsize ? *reinterpret_cast<const float4 *>(hist + xi)
+                                        : *reinterpret_cast<const float4 *>(in + (xi - irsize));
+        *reinterpret_cast<float4 *>(xs + G::xi(i)) = v;
+      }
+      for (int i = tid * 4; i < kDcKC; i += kDcThreads * 4) {
+        const int k = k0 + i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k + 3 < k_hi) {
+          v = *reinterpret_cast<const float4 *>(grev + k);
+        } else {
+          if (k < k_hi) v.x = grev[k];
+          if (k + 1 < k_hi) v.y = grev[k + 1];
+          if (k + 2 < k_hi) v.z = grev[k + 2];
+        }
+        *reinterpret_cast<float4 *>(gs + i) = v;
+      }
+    } else {
+      for (int i = tid; i < G::XS; i += kDcThreads) {
+        const int xi = t0 + k0 + i;
+        float v = 0.f;
+        if (xi < total) v = xi < irsize ? hist[xi] : in[xi - irsize];
+        xs[G::xi(i)] = v;
+      }
+      for (int i = tid; i < kDcKC; i += kDcThreads) {
+        const int k = k0 + i;
+        gs[i] = k < k_hi ? grev[k] : 0.f;
+      }
     }
     __syncthreads();
+    // ---- this warp's slice of the chunk: TN outputs per lane, 8 taps per step ----------------------------
     const int kw = warp * kDcWarpTaps;
     if (k0 + kw < k_hi) {  // warp-uniform: skip slices that are all padding
-      const float *xp = xs + lane * kDcTN + kw;
-      float xw[16];
-      {
-        float4 v0 = *reinterpret_cast<const float4 *>(xp), v1 = *reinterpret_cast<const float4 *>(xp + 4);
-        xw[0] = v0.x, xw[1] = v0.y, xw[2] = v0.z, xw[3] = v0.w, xw[4] = v1.x, xw[5] = v1.y, xw[6] = v1.z, xw[7] = v1.w;
+      const int xb = lane * TN + kw;  // logical index of this lane's first window element
+      float xw[TN + 8];
+#pragma unroll
+      for (int i = 0; i < TN; i += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(xs + G::xi(xb + i));
+        xw[i] = v.x, xw[i + 1] = v.y, xw[i + 2] = v.z, xw[i + 3] = v.w;
       }
-#pragma unroll 2
-      for (int kk = 0; kk < kDcWarpTaps; kk += 8) {
-        float4 v2 = *reinterpret_cast<const float4 *>(xp + kk + 8), v3 = *reinterpret_cast<const float4 *>(xp + kk + 12);
-        xw[8] = v2.x, xw[9] = v2.y, xw[10] = v2.z, xw[11] = v2.w, xw[12] = v3.x, xw[13] = v3.y, xw[14] = v3.z, xw[15] = v3.w;
-        float4 g0 = *reinterpret_cast<const float4 *>(gs + kw + kk), g1 = *reinterpret_cast<const float4 *>(gs + kw + kk + 4);
+#pragma unroll
+      for (int kk = 0; kk < kDcWarpTaps; kk += 8) {  // fully unrolled: the sliding window never moves registers
+        const float4 v2 = *reinterpret_cast<const float4 *>(xs + G::xi(xb + kk + TN)),
+                     v3 = *reinterpret_cast<const float4 *>(xs + G::xi(xb + kk + TN + 4));
+        xw[TN] = v2.x, xw[TN + 1] = v2.y, xw[TN + 2] = v2.z, xw[TN + 3] = v2.w;
+        xw[TN + 4] = v3.x, xw[TN + 5] = v3.y, xw[TN + 6] = v3.z, xw[TN + 7] = v3.w;
+        const float4 g0 = *reinterpret_cast<const float4 *>(gs + kw + kk), g1 = *reinterpret_cast<const float4 *>(gs + kw + kk + 4);
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; j++)
 #pragma unroll
-          for (int i = 0; i < kDcTN; i++) acc[i] = fmaf(g[j], xw[i + j], acc[i]);
+          for (int i = 0; i < TN; i++) acc[i] = fmaf(g[j], xw[i + j], acc[i]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) xw[i] = xw[i + 8];
+        for (int i = 0; i < TN; i++) xw[i] = xw[i + 8];
       }
     }
     __syncthreads();
   }
 
-  // reduce the warps' tap slices
+  // ---- reduce the warps' tap slices ------------------------------------------------------------------------
 #pragma unroll
-  for (int i = 0; i < kDcTN; i++) red[warp][lane * kDcTN + i] = acc[i];
+  for (int i = 0; i < TN; i++) red[warp][lane * TN + i] = acc[i];
   __syncthreads();
-  float sum = 0.f;  // thread `tid` owns output t0 + tid (kDcThreads == kDcTileOut)
+  for (int o = tid; o < G::TILE; o += kDcThreads) {
+    float sum = 0.f;
 #pragma unroll
-  for (int w = 0; w < kDcWarps; w++) sum += red[w][tid];
+    for (int w = 0; w < kDcWarps; w++) sum += red[w][o];
+    red[0][o] = sum;  // only this thread reads or writes column o from here on
+  }
   if (S > 1) {
-    __syncthreads();
-    red[0][tid] = sum;
     cluster.sync();
     if (rank == 0) {
-      for (int r = 1; r < S; r++) sum += cluster.map_shared_rank(&red[0][0], r)[tid];
+      for (int o = tid; o < G::TILE; o += kDcThreads) {
+        float sum = red[0][o];
+        for (int r = 1; r < S; r++) sum += cluster.map_shared_rank(&red[0][0], r)[o];
+        red[0][o] = sum;
+      }
     }
     cluster.sync();
   }
-  if (rank == 0 && t0 + tid < nout) a.out[(size_t)ch * nout + t0 + tid] = sum;
+  if (rank == 0)
+    for (int o = tid; o < G::TILE; o += kDcThreads)
+      if (t0 + o < nout) a.out[(size_t)ch * nout + t0 + o] = red[0][o];
 
   // history for the next call: the last irsize samples of xl, written to the other buffer
   if (rank == 0 && tile == 0) {
@@ -131,16 +177,25 @@ __global__ void __launch_bounds__(kDcThreads) dconv_fir_kernel(DconvArgs a) {
     }
   }
 }
-static_assert(kDcThreads == kDcTileOut, "one thread per output in the epilogue");
 
-// ring write used by the time-varying variant (cl_dconv.cpp:134-148): coefs[(wp + i) mod L] = in2[i]
-__global__ void dconv_coef_write_kernel(float *coefs, const float *in2, int vsize, int L, int wp) {
+// grev[k] = coefs[irsize-1-k] for all channels (after push_ir and after every time-varying ring write)
+__global__ void dconv_reverse_kernel(float *grev, const float *coefs, int irsize, int L) {
+  const int ch = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < irsize) grev[(size_t)ch * irsize + k] = coefs[(size_t)ch * L + irsize - 1 - k];
+}
+
+// ring write used by the time-varying variant (cl_dconv.cpp:134-148): coefs[(wp + i) mod L] = in2[i], and the
+// same value into the reversed copy when it lands on a tap position (< irsize)
+__global__ void dconv_coef_write_kernel(float *coefs, float *grev, const float *in2, int vsize, int irsize, int L, int wp) {
   const int ch = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < vsize) {
     int pos = wp + i;
     if (pos >= L) pos -= L;
-    coefs[(size_t)ch * L + pos] = in2[(size_t)ch * vsize + i];
+    const float v = in2[(size_t)ch * vsize + i];
+    coefs[(size_t)ch * L + pos] = v;
+    if (pos < irsize) grev[(size_t)ch * irsize + irsize - 1 - pos] = v;
   }
 }
 
