@@ -319,6 +319,68 @@ def bench_dconv(eng, local, steps, warmup):
     return {"ms_per_step": ms / steps, "flop_per_step": flop, "single_block_us": ms1 / 50 * 1e3}
 
 
+def bench_rfft4096(eng, local, steps, warmup):
+    """BASELINE config 2 shape, batched: 32768 x 4096-point real FFT, forward then inverse (round trip)."""
+    import torch
+
+    size, batch = 4096, 32768  # 512 MiB per direction (SURVEY 8d S2)
+    f = eng.Clrfft(local, size, True, max_batch=1)
+    i = eng.Clrfft(local, size, False, max_batch=1)
+    x = torch.rand(2, batch, size, device="cuda") * 2 - 1
+    y = torch.empty_like(x)
+
+    def step(k):
+        assert f.transform_dev(x[k % 2], y[k % 2], batch) == 0
+        assert i.transform_dev(y[k % 2], y[k % 2], batch) == 0
+
+    ms = event_time_ms(step, steps, warmup)
+    f.close()
+    i.close()
+    return {"ms_per_step": ms / steps, "bytes_per_step": 2 * batch * 8 * size}
+
+
+def bench_latency(eng, local):
+    """Per-call latency of the reference-facing synchronous host API at the reference's own shapes
+    (batch 1 / mono): what a Csound performance thread would see per call."""
+    import numpy as np
+
+    out = {}
+    rng = np.random.default_rng(0)
+
+    def timeit(fn, n=300):
+        for _ in range(20):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        return (time.perf_counter() - t0) / n * 1e6
+
+    c = eng.Clcfft(local, 1024, True)
+    x = (rng.uniform(-1, 1, 1024) + 1j * rng.uniform(-1, 1, 1024)).astype(np.complex64)
+    out["cfft1024_batch1_us"] = timeit(lambda: c.transform(x))
+    c.close()
+    f, i = eng.Clrfft(local, 4096, True), eng.Clrfft(local, 4096, False)
+    r = rng.uniform(-1, 1, 4096).astype(np.float32).view(np.complex64)
+    out["rfft4096_roundtrip_batch1_us"] = timeit(lambda: (f.transform(r), i.transform(r)))
+    f.close()
+    i.close()
+    p = eng.Clpconv(local, 96000, 512)
+    p.push_ir((rng.standard_normal(96000) * 0.01).astype(np.float32))
+    xin, yout = rng.uniform(-1, 1, 512).astype(np.float32), np.zeros(512, np.float32)
+    us = timeit(lambda: p.convolution(yout, xin))
+    out["pconv_96000x512_mono_block_us"] = us
+    out["pconv_96000x512_mono_realtime_ratio"] = (512 / SR * 1e6) / us
+    p.close()
+    d = eng.Cldconv(local, 4096, 256, channels=64)
+    d.push_ir((rng.standard_normal((64, 4096)) / 64).astype(np.float32))
+    xin, yout = rng.uniform(-1, 1, (64, 256)).astype(np.float32), np.zeros((64, 256), np.float32)
+    us = timeit(lambda: d.convolution(yout, xin))
+    out["dconv_4096x256x64ch_block_us"] = us
+    out["dconv_4096x256x64ch_realtime_ratio"] = (256 / SR * 1e6) / us
+    d.close()
+    return out
+
+
 def cpu_baseline_pconv(threads, cvs=CVS, pts=PTS, blocks=None):
     """The reference's own implementation on the host cores: `threads` channels (one per thread)."""
     import numpy as np
@@ -468,6 +530,11 @@ def main():
         gbs = c["bytes_per_step"] / (c["ms_per_step"] * 1e-3) / 1e9
         secondary["batched_cfft_1024x65536"] = {"value": gbs, "unit": "GB/s", "ms_per_step": c["ms_per_step"],
                                                 "roofline_frac": gbs / peak}
+        q = bench_rfft4096(eng, local, k, 3)
+        gbs = q["bytes_per_step"] / (q["ms_per_step"] * 1e-3) / 1e9
+        secondary["batched_rfft_4096x32768_roundtrip"] = {"value": gbs, "unit": "GB/s", "ms_per_step": q["ms_per_step"],
+                                                          "roofline_frac": gbs / peak}
+        secondary["host_api_latency"] = bench_latency(eng, local)
         d = bench_dconv(eng, local, k, 3)
         tf = d["flop_per_step"] / (d["ms_per_step"] * 1e-3) / 1e12
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
