@@ -151,7 +151,7 @@ static int launch_cfft_t(bool inv, const float2 *in, float2 *out, const float2 *
 }
 template <int LOGN>
 static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *w2, const float2 *hw,
-                         int batch, cudaStream_t st) {
+                         int batch, float fwd_scale, cudaStream_t st) {
   using B = BatchGeom<LOGN>;
   const int grid = (batch + B::TPB - 1) / B::TPB;
   if constexpr (RegSplitGeom<LOGN>::OK) {
@@ -163,7 +163,7 @@ static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *
     } else {
       int rc = set_smem(rfft_fwd_reg_kernel<LOGN>, B::SMEM_BYTES);
       if (rc) return rc;
-      rfft_fwd_reg_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, hw, batch, 1.0f / (float)(1 << LOGN));
+      rfft_fwd_reg_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, hw, batch, fwd_scale);
     }
     CK(cudaGetLastError());
     return B2F_OK;
@@ -175,7 +175,7 @@ static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *
   } else {
     int rc = set_smem(rfft_fwd_kernel<LOGN>, B::SMEM_BYTES);
     if (rc) return rc;
-    rfft_fwd_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, w2, batch);
+    rfft_fwd_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, w2, batch, fwd_scale);
   }
   CK(cudaGetLastError());
   return B2F_OK;
@@ -207,8 +207,8 @@ static int launch_cfft(int logn, bool inv, const float2 *in, float2 *out, const 
 #undef CALL
 }
 static int launch_rfft(int logn, bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *w2,
-                       const float2 *hw, int batch, cudaStream_t st) {
-#define CALL(L) launch_rfft_t<L>(inv, in, out, tw, w2, hw, batch, st)
+                       const float2 *hw, int batch, float fwd_scale, cudaStream_t st) {
+#define CALL(L) launch_rfft_t<L>(inv, in, out, tw, w2, hw, batch, fwd_scale, st)
   B2F_DISPATCH_LOGN(logn, CALL)
 #undef CALL
 }
@@ -341,13 +341,13 @@ struct LargePlan {
     if (logn == 16) return inv ? run_t<8, 8, true>(in, out, batch, scale, st) : run_t<8, 8, false>(in, out, batch, scale, st);
     return B2F_ERR_UNSUPPORTED;
   }
-  int run_real(bool inv, const float2 *in, float2 *out, const float2 *w2, int batch, cudaStream_t st) {
+  int run_real(bool inv, const float2 *in, float2 *out, const float2 *w2, int batch, float fwd_scale, cudaStream_t st) {
     const int N = 1 << logn;
     const long long pairs = (long long)batch * (N / 2);
     const int grid = (int)((pairs + 255) / 256);
     int rc;
     if (!inv) {
-      if ((rc = run_c2c(false, in, out, batch, 1.0f / (float)N, st))) return rc;
+      if ((rc = run_c2c(false, in, out, batch, fwd_scale, st))) return rc;
       rfft_split_kernel<false><<<grid, 256, 0, st>>>(out, out, w2, N, pairs);
       CK(cudaGetLastError());
     } else {
@@ -414,6 +414,8 @@ static int d2h(void *dst, const void *src, size_t bytes, Staging &sg, cudaStream
 // =====================================================================================================
 struct FftPlanCore {
   int device = 0, N = 0, logn = 0, fwd = 1, max_batch = 1;
+  bool unscaled = false;  // forward without the 1/N (what Clpconv's frames use, cl_conv_kernels.h:54-68)
+  float fwd_scale() const { return (fwd && !unscaled) ? 1.0f / (float)N : 1.0f; }
   float2 *d_tw = nullptr;   // pass twiddles (small path) or sub-plan twiddles (large path)
   float2 *d_w2 = nullptr;   // split twiddles (real plans)
   float2 *d_hw = nullptr;   // folded split table 0.5*scale*i*w2 (forward) / its conjugate, unscaled (inverse)
@@ -444,7 +446,7 @@ struct FftPlanCore {
       std::vector<float2> w2 = make_split_twiddles(N), hw((size_t)N / 2 + 1);
       rc = upload(w2, &d_w2);
       if (rc) return rc;
-      const float s = fwd ? 1.0f / (float)N : 1.0f;  // powers of two: the folding is exact
+      const float s = fwd_scale();  // powers of two: the folding is exact
       for (int i = 0; i <= N / 2 && i < N; i++) {
         // 0.5 * i * w2[i] = 0.5 * (-w.y, w.x); the inverse table is its conjugate (cl_fft.cpp:233-238 sign)
         hw[i].x = -0.5f * s * w2[i].y;
@@ -483,9 +485,9 @@ struct FftPlanCore {
     return launch_cfft(logn, !fwd, in, out, d_tw, batch, scale, st);
   }
   int run_real(const float2 *in, float2 *out, int batch, cudaStream_t st) {
-    if (cluster.ok() && fwd) return cluster.run<false, true>(in, out, d_w2, batch, 1.0f / (float)N, st);
-    if (is_large()) return large.run_real(!fwd, in, out, d_w2, batch, st);
-    return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, d_hw, batch, st);
+    if (cluster.ok() && fwd) return cluster.run<false, true>(in, out, d_w2, batch, fwd_scale(), st);
+    if (is_large()) return large.run_real(!fwd, in, out, d_w2, batch, fwd_scale(), st);
+    return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, d_hw, batch, fwd_scale(), st);
   }
 };
 
@@ -599,12 +601,22 @@ struct b2f_pconv {
   cudaStream_t stream = nullptr;
   Staging sg_in, sg_in2, sg_out;
   int cluster = 1;
+  // general path (pts > 2^kPconvMaxLogP): batched real-FFT plans + pad / MAC / overlap-add kernels
+  FftPlanCore *gfwd = nullptr, *ginv = nullptr;
+  float *d_pad = nullptr;   // [channels][2*pts]
+  float2 *d_Y = nullptr;    // [channels][pts]
+  bool general() const { return gfwd != nullptr; }
   size_t ring_elems() const { return (size_t)channels * nparts * pts; }
   void destroy() {
     cudaSetDevice(device);
     for (void *p : {(void *)d_fdl, (void *)d_irs, (void *)d_tw, (void *)d_w2, (void *)d_tail, (void *)d_in1,
-                    (void *)d_in2, (void *)d_out, (void *)d_ir})
+                    (void *)d_in2, (void *)d_out, (void *)d_ir, (void *)d_pad, (void *)d_Y})
       if (p) cudaFree(p);
+    for (FftPlanCore *p : {gfwd, ginv})
+      if (p) {
+        p->destroy();
+        delete p;
+      }
     if (stream) cudaStreamDestroy(stream);
     sg_in.release();
     sg_in2.release();
@@ -692,7 +704,7 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   *out = nullptr;
   const int logp = ilog2_exact(pts);
   if (logp < 1 || cvs < pts || channels < 1) return B2F_ERR_INVALID_VALUE;
-  if (logp > kPconvMaxLogP || channels > 65535) return B2F_ERR_UNSUPPORTED;
+  if (logp > 15 || channels > 65535) return B2F_ERR_UNSUPPORTED;  // frame = pts complex points <= 32768
   int rc = check_device(device);
   if (rc) return rc;
   b2f_pconv *h = new (std::nothrow) b2f_pconv;
@@ -713,8 +725,21 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   };
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "stream"));
-  if ((rc = upload(make_pass_twiddles(logp), &h->d_tw))) return fail(rc);
-  if ((rc = upload(make_split_twiddles(pts), &h->d_w2))) return fail(rc);
+  if (logp <= kPconvMaxLogP) {
+    if ((rc = upload(make_pass_twiddles(logp), &h->d_tw))) return fail(rc);
+    if ((rc = upload(make_split_twiddles(pts), &h->d_w2))) return fail(rc);
+  } else {
+    h->gfwd = new (std::nothrow) FftPlanCore;
+    h->ginv = new (std::nothrow) FftPlanCore;
+    if (!h->gfwd || !h->ginv) return fail(B2F_ERR_ALLOC);
+    h->gfwd->unscaled = true;  // Clpconv's frames are never scaled (cl_conv_kernels.h:54-68)
+    if ((rc = h->gfwd->init(device, pts, 1, channels, true))) return fail(rc);
+    if ((rc = h->ginv->init(device, pts, 0, channels, true))) return fail(rc);
+    if ((e = cudaMalloc((void **)&h->d_pad, (size_t)channels * 2 * pts * sizeof(float))) != cudaSuccess)
+      return fail(cuda_fail(e, "cudaMalloc pad"));
+    if ((e = cudaMalloc((void **)&h->d_Y, (size_t)channels * pts * sizeof(float2))) != cudaSuccess)
+      return fail(cuda_fail(e, "cudaMalloc Y"));
+  }
   const size_t ring = h->ring_elems() * sizeof(float2), blk = (size_t)channels * pts * sizeof(float);
   if ((e = cudaMalloc((void **)&h->d_fdl, ring)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc fdl"));
   if ((e = cudaMalloc((void **)&h->d_irs, ring)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc irs"));
@@ -746,9 +771,48 @@ extern "C" int b2f_pconv_reset(b2f_pconv *h) {
   return B2F_OK;
 }
 
+// general path: R(x) of one block per channel (x: [channels] rows of `stride` floats) into ring frame `frame`
+static int pconv_general_frame(b2f_pconv *h, const float *x, size_t stride, float2 *ring, int frame, cudaStream_t st) {
+  const int pts = h->pts;
+  dim3 grid((2 * pts + 255) / 256, h->channels, 1);
+  pconv_pad_kernel<<<grid, 256, 0, st>>>(x, stride, h->d_pad, pts);
+  CK(cudaGetLastError());
+  int rc = h->gfwd->run_real((const float2 *)h->d_pad, h->d_Y, h->channels, st);
+  if (rc) return rc;
+  CK(cudaMemcpy2DAsync(ring + (size_t)frame * pts, (size_t)h->nparts * pts * sizeof(float2), h->d_Y,
+                       (size_t)pts * sizeof(float2), (size_t)pts * sizeof(float2), h->channels,
+                       cudaMemcpyDeviceToDevice, st));
+  return B2F_OK;
+}
+static int pconv_general_push(b2f_pconv *h, const float *ir, size_t stride, cudaStream_t st) {
+  for (int i = 0; i < h->nparts; i++) {
+    int frame = (h->wp2 - i) % h->nparts;
+    if (frame < 0) frame += h->nparts;
+    int rc = pconv_general_frame(h, ir + (size_t)i * h->pts, stride, h->d_irs, frame, st);
+    if (rc) return rc;
+  }
+  return B2F_OK;
+}
+static int pconv_general_step(b2f_pconv *h, bool tv, float *d_out, const float *d_in1, const float *d_in2, cudaStream_t st) {
+  const int pts = h->pts;
+  int rc = pconv_general_frame(h, d_in1, pts, h->d_fdl, h->wp, st);
+  if (rc) return rc;
+  if (tv && (rc = pconv_general_frame(h, d_in2, pts, h->d_irs, h->wp2, st))) return rc;
+  const int rp = (h->wp + 1 == h->nparts) ? 0 : h->wp + 1;
+  dim3 gm((pts / 2 + 255) / 256, h->channels, 1);
+  pconv_mac_kernel<<<gm, 256, 0, st>>>(h->d_fdl, h->d_irs, h->d_Y, pts, h->nparts, rp);
+  CK(cudaGetLastError());
+  if ((rc = h->ginv->run_real(h->d_Y, h->d_Y, h->channels, st))) return rc;
+  dim3 go((pts + 255) / 256, h->channels, 1);
+  pconv_ola_kernel<<<go, 256, 0, st>>>((const float *)h->d_Y, h->d_tail, d_out, pts);
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
+
 extern "C" int b2f_pconv_push_ir_dev(b2f_pconv *h, const void *d_ir, size_t ir_stride, void *stream) {
   if (!h || !d_ir || ir_stride < (size_t)h->nparts * h->pts) return B2F_ERR_INVALID_VALUE;
   CK(cudaSetDevice(h->device));
+  if (h->general()) return pconv_general_push(h, (const float *)d_ir, ir_stride, (cudaStream_t)stream);
   int rc = launch_pconv_push(h->logp, (const float *)d_ir, ir_stride, h, (cudaStream_t)stream);
   // after nparts decrements the write position is back where it started (cl_conv.cpp:385)
   return rc;
@@ -760,7 +824,7 @@ extern "C" int b2f_pconv_push_ir_host(b2f_pconv *h, const float *ir, size_t ir_s
   if (!h->d_ir) CK(cudaMalloc((void **)&h->d_ir, (size_t)h->channels * per * sizeof(float)));
   CK(cudaMemcpy2DAsync(h->d_ir, per * sizeof(float), ir, ir_stride * sizeof(float), per * sizeof(float), h->channels,
                        cudaMemcpyHostToDevice, h->stream));
-  int rc = launch_pconv_push(h->logp, h->d_ir, per, h, h->stream);
+  int rc = h->general() ? pconv_general_push(h, h->d_ir, per, h->stream) : launch_pconv_push(h->logp, h->d_ir, per, h, h->stream);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return B2F_OK;
@@ -772,7 +836,8 @@ static int pconv_enqueue(b2f_pconv *h, bool tv, float *d_out, const float *d_in1
   a.in1 = d_in1, a.in2 = d_in2, a.out = d_out;
   a.tw = h->d_tw, a.w2 = h->d_w2;
   a.nparts = h->nparts, a.wp = h->wp, a.wp2 = h->wp2;
-  int rc = launch_pconv_step(h->logp, tv, a, h->channels, h->cluster, st);
+  int rc = h->general() ? pconv_general_step(h, tv, d_out, d_in1, d_in2, st)
+                        : launch_pconv_step(h->logp, tv, a, h->channels, h->cluster, st);
   if (rc) return rc;
   h->wp = h->wp != h->nparts - 1 ? h->wp + 1 : 0;             // cl_conv.cpp:424
   if (tv) h->wp2 = h->wp2 == 0 ? h->nparts - 1 : h->wp2 - 1;  // cl_conv.cpp:519

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
 template <int LOGN>
 __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
     rfft_fwd_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ w2,
-                    int batch) {
+                    int batch, float scale) {
   using B = BatchGeom<LOGN>;
   constexpr int N = 1 << LOGN;
   extern __shared__ float2 smem[];
@@ -63,7 +63,6 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   const float2 *src = in + (active ? b : 0) * N;
   float2 *dst = out + (active ? b : 0) * N;
   float2 *sm = smem + lt * FftGeom<LOGN>::SMEM;
-  const float scale = 1.0f / (float)N;
   auto load = [&](int idx, int) { return active ? src[idx] : make_float2(0.f, 0.f); };
   auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = make_float2(v.x * scale, v.y * scale); };
   fft_run<LOGN, false, true>(load, store, sm, tw, t, CtaSync());

@@ -322,4 +322,55 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS)
   for (int k = threadIdx.x; k < PTS; k += P::NTHREADS) g[k] = sX[pad_idx(k)];
 }
 
+
+// =====================================================================================================
+// General path for partitions too long for the fused kernel (pts = 8192 .. 32768, the upper half of the
+// partition sizes swept by the reference's csound/tests.py:10). The FFTs run on the batched real-FFT
+// plans (unscaled forward), the three kernels below do the rest. Per block: pad -> rFFT -> frame copy ->
+// MAC -> inverse rFFT -> overlap-add; the MAC still moves all but a few percent of the bytes.
+// =====================================================================================================
+
+// in [channels][pts] -> pad [channels][2*pts], upper half zero (cl_conv.cpp:399: half of in1 is written)
+__global__ void pconv_pad_kernel(const float *in, size_t in_stride, float *pad, int pts) {
+  const int ch = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * pts) pad[(size_t)ch * 2 * pts + i] = i < pts ? in[(size_t)ch * in_stride + i] : 0.f;
+}
+
+// Y[ch][n] = sum_p FDL[(rp+p) mod nparts][n] (*) IR[p][n], ascending p; bin 0 component-wise
+// (cl_conv_kernels.h:102-118). grid = (pts / 512, channels), 256 threads, two bins per thread.
+__global__ void __launch_bounds__(256)
+    pconv_mac_kernel(const float2 *fdl, const float2 *irs, float2 *Y, int pts, int nparts, int rp) {
+  const int ch = blockIdx.y;
+  const int q = blockIdx.x * 256 + threadIdx.x;  // float4 index inside a frame
+  const size_t stride4 = pts / 2;
+  if (q >= (int)stride4) return;
+  const size_t chan4 = (size_t)ch * nparts * stride4;
+  const float4 *F = reinterpret_cast<const float4 *>(fdl) + chan4 + q;
+  const float4 *G = reinterpret_cast<const float4 *>(irs) + chan4 + q;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 acc0 = make_float2(0.f, 0.f);
+  const int wrap = nparts - rp;  // partitions [0, wrap) read frames rp.., [wrap, nparts) read frames 0..
+  mac_segment<8>(acc, acc0, F + (size_t)rp * stride4, G, wrap, stride4);
+  mac_segment<8>(acc, acc0, F, G + (size_t)wrap * stride4, nparts - wrap, stride4);
+  if (q == 0) {
+    acc.x = acc0.x;
+    acc.y = acc0.y;
+  }
+  reinterpret_cast<float4 *>(Y)[(size_t)ch * stride4 + q] = acc;
+}
+
+// y [channels][2*pts] (inverse transform, unnormalised) -> out = (y[0,pts) + tail) / pts, tail = y[pts, 2pts)
+// (cl_conv_kernels.h:120-124)
+__global__ void pconv_ola_kernel(const float *y, float *tail, float *out, int pts) {
+  const int ch = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < pts) {
+    const float inv = 1.0f / (float)pts;
+    const size_t o = (size_t)ch * pts + n;
+    out[o] = (y[(size_t)ch * 2 * pts + n] + tail[o]) * inv;
+    tail[o] = y[(size_t)ch * 2 * pts + pts + n];
+  }
+}
+
 }  // namespace b2f

@@ -194,3 +194,37 @@ def test_reset_and_device_api(eng):
         assert d.convolution_dev(d_y2[t], d_x[t]) == 0
     torch.cuda.synchronize()
     assert np.array_equal(d_y2.cpu().numpy(), y)  # device-side push_ir == host-side push_ir
+
+
+@pytest.mark.parametrize("pts", [8192, 16384, 32768])
+def test_large_partitions_general_path(eng, port, pts):
+    """Partition sizes above 4096 (the upper half of the reference's csound/tests.py sweep) run on the general
+    path (batched real-FFT plans + MAC / overlap-add kernels) instead of the fused kernel: same semantics."""
+    nparts = 3
+    cvs = nparts * pts + 100
+    nb = 2 * nparts + 2
+    rng = np.random.default_rng(pts)
+    ir = (rng.standard_normal((2, cvs)) * 0.05).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, 2, pts)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, 2, pts)) * 0.05).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts, channels=2)
+    assert c.get_cl_err() == 0 and c.nparts == nparts
+    assert c.push_ir(ir) == 0
+    y = run_stream(c, x)
+    for ch in range(2):
+        o = port.pconv(cvs, pts)
+        o.push_ir(ir[ch])
+        assert rel_l2(c.read_spectra(2, ch), o.spec2()) < TOL
+        want = np.stack([o.convolution(x[t, ch]) for t in range(nb)])
+        assert rel_l2(y[:, ch], want) < TOL
+    # time-varying on a fresh object
+    c = eng.Clpconv(0, cvs, pts, channels=2)
+    y = run_stream(c, x, x2)
+    o = port.pconv(cvs, pts)
+    want = np.stack([o.convolution(x[t, 1], x2[t, 1]) for t in range(nb)])
+    assert rel_l2(y[:, 1], want) < TOL
+
+
+def test_partition_size_limit(eng):
+    c = eng.Clpconv(0, 1 << 18, 1 << 16, errs=lambda s, d: None)
+    assert c.get_cl_err() == 3  # frames above 32768 complex points are not implemented
