@@ -510,13 +510,13 @@ def main():
         value = r["bytes_per_step"] * world / t_step / 1e9
         unit, metric = "GB/s", "batched_rfft_GBps"
         achieved = r["bytes_per_step"] / t_step / 1e9
-        roof = {"bound": "hbm", "kernel": "large_cols_kernel + large_rows_kernel + rfft_split_kernel", "achieved": achieved,
+        roof = {"bound": "hbm", "kernel": "large_cols_kernel<7,8> + large_rows_kernel<7,8,REAL> (split fused)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("rfft65536_bytes_per_step"),
                 "algorithmic_bytes_per_launch": r["bytes_per_step"], "peak_source": peak_src}
         e2e_v = r["bytes_per_step"] * world / (r["e2e_ms_per_step"] * 1e-3) / 1e9
         e2e = {"value": e2e_v, "unit": unit, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
                "d2h_bytes_per_step": r["d2h_bytes_per_step"], "ms_per_step": r["e2e_ms_per_step"]}
-        launches = args.steps * 17  # per step: 8 chunks x (cols + rows) + split
+        launches = args.steps * 2  # per step: columns kernel + rows kernel (real split fused)
 
     secondary = {}
     if not args.no_secondary and rank == 0 and world == 1:

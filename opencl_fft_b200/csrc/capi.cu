@@ -219,8 +219,12 @@ struct ClusterPlan {
   int logn = 0, log1 = 0, max_clusters = 0;
   float2 *d_ctw1 = nullptr, *d_ctwl = nullptr;  // N1-point pass twiddles, [16][N1] inter-step table
   bool ok() const { return d_ctwl != nullptr; }
+  // Off by default: on B200 the two-kernel four-step path (fft_large.cuh) measures faster for every transform
+  // this kernel covers (real forward 2^15: 2.29 vs 2.11 TB/s; complex 2^15: 2.96 vs 2.05). Kept as the
+  // single-HBM-pass design to come back to (profiles/r01_fft_cluster_notes.md); B2F_CLUSTER_FFT=1 enables it
+  // for N = 2^15, B2F_CLUSTER_FFT_MIN_LOGN=13|14 extends it downwards.
   static bool wanted(int logn) {
-    if (getenv("B2F_NO_CLUSTER_FFT")) return false;
+    if (!getenv("B2F_CLUSTER_FFT") && !getenv("B2F_CLUSTER_FFT_MIN_LOGN")) return false;
     const char *lo = getenv("B2F_CLUSTER_FFT_MIN_LOGN");
     const int min_logn = lo ? atoi(lo) : 15;
     return logn >= min_logn && logn >= 13 && logn <= 15;
@@ -315,12 +319,12 @@ struct LargePlan {
       if (p) cudaFree(p);
     d_tw1 = d_tw2 = d_twl = d_scratch = nullptr;
   }
-  template <int L1, int L2, bool INV>
-  int run_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st) {
+  template <int L1, int L2, bool INV, bool REAL = false>
+  int run_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw = nullptr) {
     using L = LargeGeom<L1, L2>;
     int rc;
     if ((rc = set_smem(large_cols_kernel<L1, L2, INV>, L::SMEM_A))) return rc;
-    if ((rc = set_smem(large_rows_kernel<L1, L2, INV>, L::SMEM_B))) return rc;
+    if ((rc = set_smem(large_rows_kernel<L1, L2, INV, REAL>, L::SMEM_B))) return rc;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
       const int nb = batch - b0 < chunk ? batch - b0 : chunk;
       const int gxa = L::N2 / L::C, gxb = L::N1 / L::RB;
@@ -331,7 +335,7 @@ struct LargePlan {
       float2 *dst = out + (size_t)b0 * L::N;
       large_cols_kernel<L1, L2, INV><<<dim3(gxa, gya), L::THREADS, L::SMEM_A, st>>>(src, d_scratch, d_tw1, d_twl, nb);
       CK(cudaGetLastError());
-      large_rows_kernel<L1, L2, INV><<<dim3(gxb, gyb), L::THREADS, L::SMEM_B, st>>>(d_scratch, dst, d_tw2, nb, scale);
+      large_rows_kernel<L1, L2, INV, REAL><<<dim3(gxb, gyb), L::THREADS, L::SMEM_B, st>>>(d_scratch, dst, d_tw2, hw, nb, scale);
       CK(cudaGetLastError());
     }
     return B2F_OK;
@@ -341,8 +345,13 @@ struct LargePlan {
     if (logn == 16) return inv ? run_t<8, 8, true>(in, out, batch, scale, st) : run_t<8, 8, false>(in, out, batch, scale, st);
     return B2F_ERR_UNSUPPORTED;
   }
-  int run_real(bool inv, const float2 *in, float2 *out, const float2 *w2, int batch, float fwd_scale, cudaStream_t st) {
+  int run_real(bool inv, const float2 *in, float2 *out, const float2 *w2, const float2 *hw, int batch, float fwd_scale,
+               cudaStream_t st) {
     const int N = 1 << logn;
+    if (!inv && !getenv("B2F_SEPARATE_SPLIT")) {  // forward: split fused into the rows kernel
+      if (logn == 15) return run_t<7, 8, false, true>(in, out, batch, fwd_scale, st, hw);
+      if (logn == 16) return run_t<8, 8, false, true>(in, out, batch, fwd_scale, st, hw);
+    }
     const long long pairs = (long long)batch * (N / 2);
     const int grid = (int)((pairs + 255) / 256);
     int rc;
@@ -475,10 +484,7 @@ struct FftPlanCore {
   }
   int run_c2c(const float2 *in, float2 *out, int batch, cudaStream_t st) {
     const float scale = fwd ? 1.0f / (float)N : 1.0f;
-    // complex transforms: the two-kernel four-step path measures faster than the cluster kernel (2.98 vs
-    // 2.05 TB/s at N = 32768); the cluster kernel earns its keep on the real forward transform, where it also
-    // absorbs the split pass. B2F_CLUSTER_C2C=1 forces it for experiments.
-    if (cluster.ok() && (!is_large() || getenv("B2F_CLUSTER_C2C")))
+    if (cluster.ok())
       return fwd ? cluster.run<false, false>(in, out, nullptr, batch, scale, st)
                  : cluster.run<true, false>(in, out, nullptr, batch, scale, st);
     if (is_large()) return large.run_c2c(!fwd, in, out, batch, scale, st);
@@ -486,7 +492,7 @@ struct FftPlanCore {
   }
   int run_real(const float2 *in, float2 *out, int batch, cudaStream_t st) {
     if (cluster.ok() && fwd) return cluster.run<false, true>(in, out, d_w2, batch, fwd_scale(), st);
-    if (is_large()) return large.run_real(!fwd, in, out, d_w2, batch, fwd_scale(), st);
+    if (is_large()) return large.run_real(!fwd, in, out, d_w2, d_hw, batch, fwd_scale(), st);
     return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, d_hw, batch, fwd_scale(), st);
   }
 };

@@ -27,7 +27,7 @@ struct LargeGeom {
   using G1 = FftGeom<LOG1>;
   using G2 = FftGeom<LOG2>;
   static constexpr int C = 256 / G1::T;   // columns per CTA in the columns kernel
-  static constexpr int RB = 256 / G2::T;  // rows per CTA in the rows kernel
+  static constexpr int RB = 256 / G2::T;  // rows per CTA in the rows kernel (16 for N2 = 256)
   static constexpr int THREADS = 256;
   static constexpr int SMEM_A = C * G1::SMEM * (int)sizeof(float2);
   static constexpr int SMEM_B = RB * G2::SMEM * (int)sizeof(float2);
@@ -64,28 +64,88 @@ __global__ void __launch_bounds__(256)
 }
 
 // grid = (N1 / RB, batch slots). Reads scratch rows, writes out[k1 + N1*k2] * scale.
-template <int LOG1, int LOG2, bool INV>
+// REAL (forward real transform): the split of cl_fft.cpp:178-191 is fused into the write-out. A CTA then
+// owns 8 rows {8g..8g+7} and their mirrors {N1-k} (row 0 mirrors itself; its slot hosts row N1/2), so both
+// members of every pair (i, N-i) = ((k1,k2), (N1-k1, N2-1-k2)) sit in its shared memory; every pair is
+// evaluated once (folded table hw, scale included) and both members are stored, in 64-byte runs.
+template <int LOG1, int LOG2, bool INV, bool REAL>
 __global__ void __launch_bounds__(256)
-    large_rows_kernel(const float2 *scratch, float2 *out, const float2 *__restrict__ tw2, int batch, float scale) {
+    large_rows_kernel(const float2 *scratch, float2 *out, const float2 *__restrict__ tw2,
+                      const float2 *__restrict__ hw, int batch, float scale) {
   using L = LargeGeom<LOG1, LOG2>;
   constexpr int N1 = L::N1, N2 = L::N2, N = L::N, RB = L::RB, T2 = L::G2::T;
+  static_assert(!REAL || RB == 16, "mirrored row groups are 8 + 8");
   extern __shared__ float2 smem[];
   const int t = threadIdx.x % T2, row = threadIdx.x / T2;
-  const int k1base = blockIdx.x * RB;
+  const int g = blockIdx.x;
+  auto row_of = [&](int rr) -> int {
+    if (!REAL) return g * RB + rr;
+    if (rr < 8) return g * 8 + rr;
+    const int d = g * 8 + (rr - 8);
+    return d == 0 ? N1 / 2 : N1 - d;
+  };
   float2 *sm = smem + row * L::G2::SMEM;
+  const int k1_fft = row_of(row);
   for (int b = blockIdx.y; b < batch; b += gridDim.y) {
-    const float2 *src = scratch + (size_t)b * N + (size_t)(k1base + row) * N2;
+    const float2 *src = scratch + (size_t)b * N + (size_t)k1_fft * N2;
     auto load = [&](int idx, int) { return src[idx]; };
     auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = v; };
     fft_run<LOG2, INV, true>(load, store, sm, tw2, t, CtaSync());
     __syncthreads();
-    // transposed write-out: consecutive threads take consecutive rows (k1), i.e. consecutive addresses
-    float2 *dst = out + (size_t)b * N + k1base;
-    const int rr = threadIdx.x % RB;
-    const float2 *smr = smem + rr * L::G2::SMEM;
-    for (int k2 = threadIdx.x / RB; k2 < N2; k2 += L::THREADS / RB) {
-      float2 v = smr[pad_idx(k2)];
-      dst[(size_t)k2 * N1 + rr] = make_float2(v.x * scale, v.y * scale);
+    float2 *dst = out + (size_t)b * N;
+    if (!REAL) {
+      // transposed write-out: consecutive threads take consecutive rows (k1), i.e. consecutive addresses
+      const int rr = threadIdx.x % RB;
+      const float2 *smr = smem + rr * L::G2::SMEM;
+      for (int k2 = threadIdx.x / RB; k2 < N2; k2 += L::THREADS / RB) {
+        float2 v = smr[pad_idx(k2)];
+        dst[(size_t)k2 * N1 + g * RB + rr] = make_float2(v.x * scale, v.y * scale);
+      }
+    } else {
+      // one pair per (direct row rr < 8, k2): low member i = k1 + N1*k2 when i < N/2, else its partner is
+      const int rr = threadIdx.x % 8;
+      const int k1 = g * 8 + rr;              // direct row, in [0, N1/2)
+      const bool zero = (k1 == 0);
+      const int prr = zero ? 0 : rr + 8;      // row 0 pairs with itself
+      const int k1p = zero ? 0 : N1 - k1;
+      const float2 *smr = smem + rr * L::G2::SMEM, *smp = smem + prr * L::G2::SMEM;
+      const float hs = 0.5f * scale;
+      // rows 1..N1/2-1: all N2 values of k2, the pair's other member is on the mirror row.
+      // row 0: pairs (0,k2) <-> (0,N2-k2) for k2 in [1, N2/2), plus the two self-paired elements.
+      for (int k2 = threadIdx.x / 8; k2 < N2; k2 += L::THREADS / 8) {
+        const int pk2 = zero ? N2 - k2 : N2 - 1 - k2;
+        if (zero && (k2 == 0 || k2 >= N2 / 2)) {
+          if (k2 == 0) {
+            const float2 v = smr[pad_idx(0)];
+            dst[0] = make_float2((v.x + v.y) * hs, (v.x - v.y) * hs);
+          } else if (k2 == N2 / 2) {
+            const float2 v = smr[pad_idx(k2)];
+            dst[N / 2] = make_float2(v.x * scale, v.y * scale);  // never visited by the reference (Q3)
+          }
+          continue;
+        }
+        float2 a = smr[pad_idx(k2)], bb = smp[pad_idx(pk2)];
+        const int i = k1 + N1 * k2, j = k1p + N1 * pk2;  // i + j == N
+        if (i < j) {
+          rfft_pair_folded<false>(a, bb, __ldg(&hw[i]), hs);
+        } else {
+          rfft_pair_folded<false>(bb, a, __ldg(&hw[j]), hs);
+        }
+        dst[i] = a;
+        dst[j] = bb;
+      }
+      // the self-mirrored row N1/2 lives in slot 8 of group 0: pairs (N1/2,k2) <-> (N1/2, N2-1-k2)
+      if (g == 0) {
+        const float2 *smh = smem + 8 * L::G2::SMEM;
+        for (int k2 = threadIdx.x; k2 < N2 / 2; k2 += L::THREADS) {
+          const int pk2 = N2 - 1 - k2;
+          float2 a = smh[pad_idx(k2)], bb = smh[pad_idx(pk2)];
+          const int i = N1 / 2 + N1 * k2, j = N1 / 2 + N1 * pk2;
+          rfft_pair_folded<false>(a, bb, __ldg(&hw[i]), hs);
+          dst[i] = a;
+          dst[j] = bb;
+        }
+      }
     }
     __syncthreads();
   }

@@ -165,12 +165,16 @@ def test_device_pointer_api_matches_host_api(eng):
     assert torch.equal(d2, d_in)
 
 
+@pytest.mark.parametrize("cluster", [False, True])
 @pytest.mark.parametrize("batch", [1, 5, 71, 300])
-def test_cluster_fft_every_transform_of_a_batch(eng, batch):
-    """The 65536-point real / 32768-point complex transforms run on 4-CTA clusters that exchange data through
-    distributed shared memory with fence-free barriers; a persistent cluster loops over several transforms
-    when batch > resident clusters. Check EVERY transform of the batch (a race shows up as a few wrong ones),
-    twice, and that the two runs agree bit for bit."""
+def test_large_fft_every_transform_of_a_batch(eng, batch, cluster, monkeypatch):
+    """The 65536-point real / 32768-point complex transforms: by default two long launches (columns, rows with
+    the real split fused); with B2F_CLUSTER_FFT=1 the single-pass kernel on 4-CTA clusters that exchange data
+    through distributed shared memory (a persistent cluster loops over several transforms when batch >
+    resident clusters). Check EVERY transform of the batch (a race shows up as a few wrong ones), twice, and
+    that the two runs agree bit for bit."""
+    if cluster:
+        monkeypatch.setenv("B2F_CLUSTER_FFT", "1")  # read when the plan is created
     size = 65536
     rng = np.random.default_rng(batch)
     x = rng.uniform(-1, 1, (batch, size)).astype(np.float32)
