@@ -19,6 +19,10 @@
 
 #include "fft_core.cuh"
 
+#ifndef LARGE_COLS_MINB
+#define LARGE_COLS_MINB 1  // measured: forcing 3 or 4 CTAs/SM (80/64 registers, spills) is 20-25 % slower
+#endif
+
 namespace b2f {
 
 template <int LOG1, int LOG2>
@@ -35,7 +39,7 @@ struct LargeGeom {
 
 // grid = (N2 / C, batch slots). twl: [N1][N2] table, twl[k1*N2 + n2] = W_N^(n2*k1) (forward sign).
 template <int LOG1, int LOG2, bool INV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LARGE_COLS_MINB)
     large_cols_kernel(const float2 *in, float2 *scratch, const float2 *__restrict__ tw1,
                       const float2 *__restrict__ twl, int batch) {
   using L = LargeGeom<LOG1, LOG2>;
