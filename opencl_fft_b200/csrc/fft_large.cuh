@@ -34,7 +34,11 @@ struct LargeGeom {
   static constexpr int RB = 256 / G2::T;  // rows per CTA in the rows kernel (16 for N2 = 256)
   static constexpr int THREADS = 256;
   static constexpr int SMEM_A = C * G1::SMEM * (int)sizeof(float2);
-  static constexpr int SMEM_B = RB * G2::SMEM * (int)sizeof(float2);
+  // rows kernel: per-row stride in float2. Odd (== 1 mod 16) for the complex write-out, where a half-warp
+  // reads one element from each of 16 rows; == 2 (mod 16) for the real write-out, where a half-warp reads two
+  // adjacent elements from each of 8 rows
+  static constexpr int ROWSTRIDE_C = G2::SMEM, ROWSTRIDE_R = G2::SMEM + 1;
+  static constexpr int SMEM_B = RB * (G2::SMEM + 1) * (int)sizeof(float2);
 };
 
 // grid = (N2 / C, batch slots). twl: [N1][N2] table, twl[k1*N2 + n2] = W_N^(n2*k1) (forward sign).
@@ -88,7 +92,8 @@ __global__ void __launch_bounds__(256)
     const int d = g * 8 + (rr - 8);
     return d == 0 ? N1 / 2 : N1 - d;
   };
-  float2 *sm = smem + row * L::G2::SMEM;
+  constexpr int RS = REAL ? L::ROWSTRIDE_R : L::ROWSTRIDE_C;
+  float2 *sm = smem + row * RS;
   const int k1_fft = row_of(row);
   for (int b = blockIdx.y; b < batch; b += gridDim.y) {
     const float2 *src = scratch + (size_t)b * N + (size_t)k1_fft * N2;
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(256)
     if (!REAL) {
       // transposed write-out: consecutive threads take consecutive rows (k1), i.e. consecutive addresses
       const int rr = threadIdx.x % RB;
-      const float2 *smr = smem + rr * L::G2::SMEM;
+      const float2 *smr = smem + rr * RS;
       for (int k2 = threadIdx.x / RB; k2 < N2; k2 += L::THREADS / RB) {
         float2 v = smr[pad_idx(k2)];
         dst[(size_t)k2 * N1 + g * RB + rr] = make_float2(v.x * scale, v.y * scale);
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(256)
       const bool zero = (k1 == 0);
       const int prr = zero ? 0 : rr + 8;      // row 0 pairs with itself
       const int k1p = zero ? 0 : N1 - k1;
-      const float2 *smr = smem + rr * L::G2::SMEM, *smp = smem + prr * L::G2::SMEM;
+      const float2 *smr = smem + rr * RS, *smp = smem + prr * RS;
       const float hs = 0.5f * scale;
       // rows 1..N1/2-1: all N2 values of k2, the pair's other member is on the mirror row.
       // row 0: pairs (0,k2) <-> (0,N2-k2) for k2 in [1, N2/2), plus the two self-paired elements.
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(256)
       }
       // the self-mirrored row N1/2 lives in slot 8 of group 0: pairs (N1/2,k2) <-> (N1/2, N2-1-k2)
       if (g == 0) {
-        const float2 *smh = smem + 8 * L::G2::SMEM;
+        const float2 *smh = smem + 8 * RS;
         for (int k2 = threadIdx.x; k2 < N2 / 2; k2 += L::THREADS) {
           const int pk2 = N2 - 1 - k2;
           float2 a = smh[pad_idx(k2)], bb = smh[pad_idx(pk2)];
