@@ -381,6 +381,30 @@ def bench_latency(eng, local):
     return out
 
 
+def cpu_reference_latency():
+    """The same four calls on the CPU reference (one thread, plan / object construction excluded)."""
+    import numpy as np
+
+    import oracle
+
+    impl = oracle.best()
+    rng = np.random.default_rng(0)
+    out = {"kind": impl.kind}
+    x = (rng.uniform(-1, 1, (200, 1024)) + 1j * rng.uniform(-1, 1, (200, 1024))).astype(np.complex64)
+    out["cfft1024_batch1_us"] = impl.cfft_run(x, True, 1)[0] / 200 * 1e6
+    r = rng.uniform(-1, 1, (100, 4096)).astype(np.float32)
+    secs, spec = impl.rfft_run(r, True, 1)
+    out["rfft4096_roundtrip_batch1_us"] = (secs + impl.rfft_run(spec, False, 1)[0]) / 100 * 1e6
+    ir = (rng.standard_normal((1, 96000)) * 0.01).astype(np.float32)
+    xs = rng.uniform(-1, 1, (1, 40 * 512)).astype(np.float32)
+    out["pconv_96000x512_mono_block_us"] = impl.pconv_run(96000, 512, ir, xs, 1)[0] / 40 * 1e6
+    h = (rng.standard_normal((1, 4096)) / 64).astype(np.float32)
+    xd = rng.uniform(-1, 1, (1, 20 * 256)).astype(np.float32)
+    # 64 channels on one thread, as a single Csound performance thread would run them
+    out["dconv_4096x256x64ch_block_us"] = impl.dconv_run(4096, 256, h, xd, 1)[0] / 20 * 64 * 1e6
+    return out
+
+
 def cpu_baseline_pconv(threads, cvs=CVS, pts=PTS, blocks=None):
     """The reference's own implementation on the host cores: `threads` channels (one per thread)."""
     import numpy as np
@@ -535,6 +559,8 @@ def main():
         secondary["batched_rfft_4096x32768_roundtrip"] = {"value": gbs, "unit": "GB/s", "ms_per_step": q["ms_per_step"],
                                                           "roofline_frac": gbs / peak}
         secondary["host_api_latency"] = bench_latency(eng, local)
+        if not args.no_cpu_baseline:
+            secondary["host_api_latency"]["cpu_reference_1_thread"] = cpu_reference_latency()
         d = bench_dconv(eng, local, k, 3)
         tf = d["flop_per_step"] / (d["ms_per_step"] * 1e-3) / 1e12
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12

@@ -392,6 +392,19 @@ struct Staging {
 };
 static const size_t kBounceMax = 1u << 20;
 
+// Low-latency path of the synchronous host entry points: when a call moves at most this
+// many bytes each way (one block of a few channels, one small transform -- what a Csound performance thread
+// does every k-cycle), the kernel reads its input from and writes its result to the PINNED bounce buffers
+// directly (they are device-accessible under unified addressing), so the call is: memcpy in, ONE launch,
+// one stream synchronise, memcpy out -- no DMA copies to set up and wait for. B2F_ZEROCOPY_MAX=0 disables it.
+static size_t zerocopy_max() {
+  static size_t v = [] {
+    const char *e = getenv("B2F_ZEROCOPY_MAX");
+    return e ? (size_t)atoll(e) : (size_t)65536;
+  }();
+  return v;
+}
+
 static int h2d(void *dst, const void *src, size_t bytes, Staging &sg, cudaStream_t st) {
   if (bytes <= kBounceMax) {
     int rc = sg.ensure(kBounceMax);
@@ -543,6 +556,14 @@ extern "C" int b2f_cfft_exec_host(b2f_cfft *plan, float *cdata, int batch) {
   int rc = c.ensure_buf();
   if (rc) return rc;
   const size_t bytes = (size_t)batch * c.N * sizeof(float2);
+  if (bytes <= zerocopy_max()) {
+    if ((rc = c.sg_in.ensure(kBounceMax)) || (rc = c.sg_out.ensure(kBounceMax))) return rc;
+    memcpy(c.sg_in.pin, cdata, bytes);
+    if ((rc = c.run_c2c((const float2 *)c.sg_in.pin, (float2 *)c.sg_out.pin, batch, c.stream))) return rc;
+    CK(cudaStreamSynchronize(c.stream));
+    memcpy(cdata, c.sg_out.pin, bytes);
+    return B2F_OK;
+  }
   if ((rc = h2d(c.d_buf, cdata, bytes, c.sg_in, c.stream))) return rc;
   if ((rc = c.run_c2c(c.d_buf, c.d_buf, batch, c.stream))) return rc;
   return d2h(cdata, c.d_buf, bytes, c.sg_out, c.stream);
@@ -589,6 +610,15 @@ extern "C" int b2f_rfft_exec_host(b2f_rfft *plan, float *cdata, float *r, int ba
   const size_t bytes = (size_t)batch * c.N * sizeof(float2);
   // forward reads the reals (cl_fft.cpp:273-275), inverse reads the spectrum (284)
   const void *src = c.fwd ? (const void *)r : (const void *)cdata;
+  if (bytes <= zerocopy_max()) {
+    if ((rc = c.sg_in.ensure(kBounceMax)) || (rc = c.sg_out.ensure(kBounceMax))) return rc;
+    memcpy(c.sg_in.pin, src, bytes);
+    if ((rc = c.run_real((const float2 *)c.sg_in.pin, (float2 *)c.sg_out.pin, batch, c.stream))) return rc;
+    CK(cudaStreamSynchronize(c.stream));
+    memcpy(cdata, c.sg_out.pin, bytes);                                    // 281 / 290
+    if (!c.fwd && (void *)r != (void *)cdata) memcpy(r, cdata, bytes);     // 292-293
+    return B2F_OK;
+  }
   if ((rc = h2d(c.d_buf, src, bytes, c.sg_in, c.stream))) return rc;
   if ((rc = c.run_real(c.d_buf, c.d_buf, batch, c.stream))) return rc;
   if ((rc = d2h(cdata, c.d_buf, bytes, c.sg_out, c.stream))) return rc;       // 281 / 290
@@ -872,6 +902,14 @@ extern "C" int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in)
   int rc = pconv_host_bufs(h, false);
   if (rc) return rc;
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
+  if (blk <= zerocopy_max()) {
+    if ((rc = h->sg_in.ensure(kBounceMax)) || (rc = h->sg_out.ensure(kBounceMax))) return rc;
+    memcpy(h->sg_in.pin, in, blk);
+    if ((rc = pconv_enqueue(h, false, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, nullptr, h->stream))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->sg_out.pin, blk);
+    return B2F_OK;
+  }
   if ((rc = h2d(h->d_in1, in, blk, h->sg_in, h->stream))) return rc;
   if ((rc = pconv_enqueue(h, false, h->d_out, h->d_in1, nullptr, h->stream))) return rc;
   return d2h(out, h->d_out, blk, h->sg_out, h->stream);
@@ -882,6 +920,18 @@ extern "C" int b2f_pconv_process_tv_host(b2f_pconv *h, float *out, const float *
   int rc = pconv_host_bufs(h, true);
   if (rc) return rc;
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
+  if (blk <= zerocopy_max()) {
+    if ((rc = h->sg_in.ensure(kBounceMax)) || (rc = h->sg_in2.ensure(kBounceMax)) || (rc = h->sg_out.ensure(kBounceMax)))
+      return rc;
+    memcpy(h->sg_in.pin, in1, blk);
+    memcpy(h->sg_in2.pin, in2, blk);
+    if ((rc = pconv_enqueue(h, true, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, (const float *)h->sg_in2.pin,
+                            h->stream)))
+      return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->sg_out.pin, blk);
+    return B2F_OK;
+  }
   if ((rc = h2d(h->d_in1, in1, blk, h->sg_in, h->stream))) return rc;
   if ((rc = h2d(h->d_in2, in2, blk, h->sg_in2, h->stream))) return rc;
   if ((rc = pconv_enqueue(h, true, h->d_out, h->d_in1, h->d_in2, h->stream))) return rc;
@@ -1062,6 +1112,14 @@ extern "C" int b2f_dconv_process_host(b2f_dconv *h, float *out, const float *in,
   int rc = dconv_host_bufs(h, false);
   if (rc) return rc;
   const size_t bytes = (size_t)h->channels * nblocks * h->vsize * sizeof(float);
+  if (bytes <= zerocopy_max()) {
+    if ((rc = h->sg_in.ensure(kBounceMax)) || (rc = h->sg_out.ensure(kBounceMax))) return rc;
+    memcpy(h->sg_in.pin, in, bytes);
+    if ((rc = dconv_enqueue(h, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, nblocks, h->stream))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->sg_out.pin, bytes);
+    return B2F_OK;
+  }
   if ((rc = h2d(h->d_in1, in, bytes, h->sg_in, h->stream))) return rc;
   if ((rc = dconv_enqueue(h, h->d_out, h->d_in1, nblocks, h->stream))) return rc;
   return d2h(out, h->d_out, bytes, h->sg_out, h->stream);
@@ -1072,6 +1130,17 @@ extern "C" int b2f_dconv_process_tv_host(b2f_dconv *h, float *out, const float *
   int rc = dconv_host_bufs(h, true);
   if (rc) return rc;
   const size_t bytes = (size_t)h->channels * h->vsize * sizeof(float);
+  if (bytes <= zerocopy_max()) {
+    if ((rc = h->sg_in.ensure(kBounceMax)) || (rc = h->sg_in2.ensure(kBounceMax)) || (rc = h->sg_out.ensure(kBounceMax)))
+      return rc;
+    memcpy(h->sg_in.pin, in1, bytes);
+    memcpy(h->sg_in2.pin, in2, bytes);
+    if ((rc = dconv_coef_write(h, (const float *)h->sg_in2.pin, h->stream))) return rc;
+    if ((rc = dconv_enqueue(h, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, 1, h->stream))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->sg_out.pin, bytes);
+    return B2F_OK;
+  }
   if ((rc = h2d(h->d_in1, in1, bytes, h->sg_in, h->stream))) return rc;
   if ((rc = h2d(h->d_in2, in2, bytes, h->sg_in2, h->stream))) return rc;
   if ((rc = dconv_coef_write(h, h->d_in2, h->stream))) return rc;
