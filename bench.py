@@ -563,9 +563,15 @@ def main():
             secondary["host_api_latency"]["cpu_reference_1_thread"] = cpu_reference_latency()
         d = bench_dconv(eng, local, k, 3)
         tf = d["flop_per_step"] / (d["ms_per_step"] * 1e-3) / 1e12
-        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        fp32_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        fp32_peak, fp32_src = fp32_nominal, "nominal"
+        pk = os.path.join(ROOT, "profiles", "fp32_peak.json")
+        if os.path.exists(pk):
+            fp32_peak, fp32_src = float(json.load(open(pk))["fp32_fma_tflops"]), "measured (tools/fma_peak.cu, profiles/fp32_peak.json)"
         secondary["dconv_4096x256x64ch"] = {"value": tf, "unit": "TFLOP/s fp32", "ms_per_step": d["ms_per_step"],
-                                            "fp32_peak_nominal": fp32_peak, "fp32_frac": tf / fp32_peak,
+                                            "roofline": {"bound": "fp32_fma", "achieved": tf, "peak": fp32_peak,
+                                                         "unit": "TFLOP/s", "frac": tf / fp32_peak, "peak_source": fp32_src},
+                                            "fp32_peak_nominal": fp32_nominal,
                                             "realtime_channels_48k": 64 * (375 * 256 / SR) / (d["ms_per_step"] * 1e-3),
                                             "single_block_latency_us": d["single_block_us"]}
 
