@@ -19,6 +19,12 @@
 
 #include "fft_core.cuh"
 
+// Build-time knobs kept for re-measurement. Measured on B200 (2048 x 32768 complex): twiddles in registers or
+// streamed from L2 at 2 CTAs/SM: 0.365 ms either way; 3 or 4 CTAs/SM (streamed twiddles, no spills): 0.43 ms --
+// more resident column CTAs mean more concurrent 2 KB-strided streams and the memory system likes that less.
+#ifndef LARGE_COLS_TW_REGS
+#define LARGE_COLS_TW_REGS 1
+#endif
 #ifndef LARGE_COLS_MINB
 #define LARGE_COLS_MINB 1  // measured: forcing 3 or 4 CTAs/SM (80/64 registers, spills) is 20-25 % slower
 #endif
@@ -52,6 +58,7 @@ __global__ void __launch_bounds__(256, LARGE_COLS_MINB)
   const int c = threadIdx.x % C, t = threadIdx.x / C;
   const int n2 = blockIdx.x * C + c;
   float2 *sm = smem + c * L::G1::SMEM;
+#if LARGE_COLS_TW_REGS
   // this thread's inter-step twiddles, fixed for every transform of the batch
   float2 wreg[E];
 #pragma unroll
@@ -61,11 +68,20 @@ __global__ void __launch_bounds__(256, LARGE_COLS_MINB)
     if (INV) w.y = -w.y;
     wreg[s] = w;
   }
+#endif
   for (int b = blockIdx.y; b < batch; b += gridDim.y) {
     const float2 *src = in + (size_t)b * N + n2;
     float2 *dst = scratch + (size_t)b * N + n2;
     auto load = [&](int idx, int) { return src[(size_t)idx * N2]; };
+#if LARGE_COLS_TW_REGS
     auto store = [&](int idx, float2 v, int slot) { dst[(size_t)idx * N2] = cmul(v, wreg[slot]); };
+#else
+    auto store = [&](int idx, float2 v, int) {
+      float2 w = __ldg(&twl[(size_t)idx * N2 + n2]);
+      if (INV) w.y = -w.y;
+      dst[(size_t)idx * N2] = cmul(v, w);
+    };
+#endif
     fft_run<LOG1, INV>(load, store, sm, tw1, t, CtaSync());
     __syncthreads();  // shared memory is reused by the next transform
   }
