@@ -375,13 +375,16 @@ struct LargePlan {
 struct Staging {
   void *pin = nullptr;
   size_t cap = 0;
+  // grow-only, sized to what the handle actually moves (an application following the reference's usage
+  // creates one object per channel: 64 objects must not pin 64 x 3 MB)
   int ensure(size_t bytes) {
     if (bytes <= cap) return B2F_OK;
     if (pin) cudaFreeHost(pin);
     pin = nullptr;
     cap = 0;
-    CK(cudaMallocHost(&pin, bytes));
-    cap = bytes;
+    const size_t want = (bytes + 4095) & ~(size_t)4095;
+    CK(cudaMallocHost(&pin, want));
+    cap = want;
     return B2F_OK;
   }
   void release() {
@@ -407,7 +410,7 @@ static size_t zerocopy_max() {
 
 static int h2d(void *dst, const void *src, size_t bytes, Staging &sg, cudaStream_t st) {
   if (bytes <= kBounceMax) {
-    int rc = sg.ensure(kBounceMax);
+    int rc = sg.ensure(bytes);
     if (rc) return rc;
     memcpy(sg.pin, src, bytes);
     CK(cudaMemcpyAsync(dst, sg.pin, bytes, cudaMemcpyHostToDevice, st));
@@ -419,7 +422,7 @@ static int h2d(void *dst, const void *src, size_t bytes, Staging &sg, cudaStream
 // blocking: returns when dst holds the data
 static int d2h(void *dst, const void *src, size_t bytes, Staging &sg, cudaStream_t st) {
   if (bytes <= kBounceMax) {
-    int rc = sg.ensure(kBounceMax);
+    int rc = sg.ensure(bytes);
     if (rc) return rc;
     CK(cudaMemcpyAsync(sg.pin, src, bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -557,7 +560,7 @@ extern "C" int b2f_cfft_exec_host(b2f_cfft *plan, float *cdata, int batch) {
   if (rc) return rc;
   const size_t bytes = (size_t)batch * c.N * sizeof(float2);
   if (bytes <= zerocopy_max()) {
-    if ((rc = c.sg_in.ensure(kBounceMax)) || (rc = c.sg_out.ensure(kBounceMax))) return rc;
+    if ((rc = c.sg_in.ensure(bytes)) || (rc = c.sg_out.ensure(bytes))) return rc;
     memcpy(c.sg_in.pin, cdata, bytes);
     if ((rc = c.run_c2c((const float2 *)c.sg_in.pin, (float2 *)c.sg_out.pin, batch, c.stream))) return rc;
     CK(cudaStreamSynchronize(c.stream));
@@ -611,7 +614,7 @@ extern "C" int b2f_rfft_exec_host(b2f_rfft *plan, float *cdata, float *r, int ba
   // forward reads the reals (cl_fft.cpp:273-275), inverse reads the spectrum (284)
   const void *src = c.fwd ? (const void *)r : (const void *)cdata;
   if (bytes <= zerocopy_max()) {
-    if ((rc = c.sg_in.ensure(kBounceMax)) || (rc = c.sg_out.ensure(kBounceMax))) return rc;
+    if ((rc = c.sg_in.ensure(bytes)) || (rc = c.sg_out.ensure(bytes))) return rc;
     memcpy(c.sg_in.pin, src, bytes);
     if ((rc = c.run_real((const float2 *)c.sg_in.pin, (float2 *)c.sg_out.pin, batch, c.stream))) return rc;
     CK(cudaStreamSynchronize(c.stream));
@@ -903,7 +906,7 @@ extern "C" int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in)
   if (rc) return rc;
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
   if (blk <= zerocopy_max()) {
-    if ((rc = h->sg_in.ensure(kBounceMax)) || (rc = h->sg_out.ensure(kBounceMax))) return rc;
+    if ((rc = h->sg_in.ensure(blk)) || (rc = h->sg_out.ensure(blk))) return rc;
     memcpy(h->sg_in.pin, in, blk);
     if ((rc = pconv_enqueue(h, false, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, nullptr, h->stream))) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -921,8 +924,7 @@ extern "C" int b2f_pconv_process_tv_host(b2f_pconv *h, float *out, const float *
   if (rc) return rc;
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
   if (blk <= zerocopy_max()) {
-    if ((rc = h->sg_in.ensure(kBounceMax)) || (rc = h->sg_in2.ensure(kBounceMax)) || (rc = h->sg_out.ensure(kBounceMax)))
-      return rc;
+    if ((rc = h->sg_in.ensure(blk)) || (rc = h->sg_in2.ensure(blk)) || (rc = h->sg_out.ensure(blk))) return rc;
     memcpy(h->sg_in.pin, in1, blk);
     memcpy(h->sg_in2.pin, in2, blk);
     if ((rc = pconv_enqueue(h, true, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, (const float *)h->sg_in2.pin,
@@ -1113,7 +1115,7 @@ extern "C" int b2f_dconv_process_host(b2f_dconv *h, float *out, const float *in,
   if (rc) return rc;
   const size_t bytes = (size_t)h->channels * nblocks * h->vsize * sizeof(float);
   if (bytes <= zerocopy_max()) {
-    if ((rc = h->sg_in.ensure(kBounceMax)) || (rc = h->sg_out.ensure(kBounceMax))) return rc;
+    if ((rc = h->sg_in.ensure(bytes)) || (rc = h->sg_out.ensure(bytes))) return rc;
     memcpy(h->sg_in.pin, in, bytes);
     if ((rc = dconv_enqueue(h, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, nblocks, h->stream))) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -1131,8 +1133,7 @@ extern "C" int b2f_dconv_process_tv_host(b2f_dconv *h, float *out, const float *
   if (rc) return rc;
   const size_t bytes = (size_t)h->channels * h->vsize * sizeof(float);
   if (bytes <= zerocopy_max()) {
-    if ((rc = h->sg_in.ensure(kBounceMax)) || (rc = h->sg_in2.ensure(kBounceMax)) || (rc = h->sg_out.ensure(kBounceMax)))
-      return rc;
+    if ((rc = h->sg_in.ensure(bytes)) || (rc = h->sg_in2.ensure(bytes)) || (rc = h->sg_out.ensure(bytes))) return rc;
     memcpy(h->sg_in.pin, in1, bytes);
     memcpy(h->sg_in2.pin, in2, bytes);
     if ((rc = dconv_coef_write(h, (const float *)h->sg_in2.pin, h->stream))) return rc;
