@@ -123,4 +123,4 @@ def test_csound_opcode_layer_compiles_against_our_headers():
     errors = [ln for ln in res.stderr.splitlines() if " error: " in ln]
     lines = sorted(int(e.split(":")[1]) for e in errors)
     assert lines == [79, 87, 135, 143], res.stderr
-    assert all("'i' was not declared" in e for e in errors)
+    assert all("was not declared in this scope" in e for e in errors)
