@@ -172,8 +172,17 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS) pconv_step_kernel(P
   // oldest frame. Partition p pairs FDL frame (rp+p) mod nparts with IR frame p; p = nparts-1 is the
   // frame just written. In TV mode IR frame wp2 is also new.
   const int rp = (a.wp + 1 == nparts) ? 0 : a.wp + 1;
-  const int p_lo = (int)((long long)rank * nparts / S);
-  const int p_hi = (int)((long long)(rank + 1) * nparts / S);
+  // Rank 0 also runs the serial part (forward FFT before, unsplit + inverse FFT + overlap-add after), so in a
+  // cluster of 4 or more it takes no regular partitions at all: the other ranks share them and rank 0's FFT
+  // overlaps their streaming instead of preceding its own.
+  int p_lo, p_hi;
+  if (S >= 4) {
+    p_lo = rank == 0 ? 0 : (int)((long long)(rank - 1) * nparts / (S - 1));
+    p_hi = rank == 0 ? 0 : (int)((long long)rank * nparts / (S - 1));
+  } else {
+    p_lo = (int)((long long)rank * nparts / S);
+    p_hi = (int)((long long)(rank + 1) * nparts / S);
+  }
   const int p_newx = nparts - 1;
   const int p_newg = TV ? a.wp2 : -1;
   const size_t stride4 = HALF;
