@@ -752,10 +752,14 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   h->nparts = cvs / pts;  // truncating, cl_conv.cpp:143
   h->wp = 0;
   h->wp2 = h->nparts - 1;
-  // enough CTAs to cover the 148 SMs twice when there are few channels: split the partitions over a
-  // thread-block cluster (portable size limit 8)
+  // Cluster split of the partitions (portable cluster limit 8), from measurements on B200 (tools/pconv_sweep.py):
+  // few channels -> enough CTAs to give every SM one; many channels with long IRs -> up to ~2048 CTAs as long as
+  // every CTA keeps >= 256 partitions to stream (1024 ch x 937 partitions: S=2 is 3 % faster than S=1 or 4;
+  // 256 ch x 187 partitions: S=1 beats S=2 by 15 %, the cluster barrier and DSMEM reduction are not free).
   int S = 1;
-  while (S < 8 && channels * S < 296 && S * 2 <= h->nparts) S *= 2;
+  while (S < 8 && channels * S < 148 && S * 2 <= h->nparts) S *= 2;
+  while (S < 8 && channels * S < 2048 && h->nparts / (2 * S) >= 256) S *= 2;
+  if (const char *e = getenv("B2F_PCONV_CLUSTER")) S = atoi(e);
   h->cluster = S;
   auto fail = [&](int code) {
     h->destroy();
