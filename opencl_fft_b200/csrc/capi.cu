@@ -487,7 +487,7 @@ struct FftPlanCore {
     return B2F_OK;
   }
   void destroy() {
-    cudaSetDevice(device);
+    if (cudaSetDevice(device) != cudaSuccess) (void)cudaGetLastError();  // never leave a stale error behind
     if (d_tw) cudaFree(d_tw);
     if (d_w2) cudaFree(d_w2);
     if (d_hw) cudaFree(d_hw);
@@ -647,7 +647,7 @@ struct b2f_pconv {
   bool general() const { return gfwd != nullptr; }
   size_t ring_elems() const { return (size_t)channels * nparts * pts; }
   void destroy() {
-    cudaSetDevice(device);
+    if (cudaSetDevice(device) != cudaSuccess) (void)cudaGetLastError();  // never leave a stale error behind
     for (void *p : {(void *)d_fdl, (void *)d_irs, (void *)d_tw, (void *)d_w2, (void *)d_tail, (void *)d_in1,
                     (void *)d_in2, (void *)d_out, (void *)d_ir, (void *)d_pad, (void *)d_Y})
       if (p) cudaFree(p);
@@ -966,7 +966,7 @@ struct b2f_dconv {
   Staging sg_in, sg_in2, sg_out;
   int L() const { return irsize + vsize; }
   void destroy() {
-    cudaSetDevice(device);
+    if (cudaSetDevice(device) != cudaSuccess) (void)cudaGetLastError();  // never leave a stale error behind
     for (void *p : {(void *)d_hist[0], (void *)d_hist[1], (void *)d_coefs, (void *)d_grev, (void *)d_in1, (void *)d_in2,
                     (void *)d_out})
       if (p) cudaFree(p);

@@ -106,3 +106,42 @@ def test_cfg4_64_channels_multiblock_equals_block_by_block(eng, port):
     assert a.convolution(ya2, x2, nblocks=nb) == 0
     full = np.convolve(np.r_[x[5], x2[5]].astype(np.float64), ir[5].astype(np.float64))[: 2 * nb * vsize]
     assert rel_l2(np.r_[ya[5], ya2[5]], np.r_[0.0, full[:-1]]) < 2e-6
+
+
+def test_time_varying_multichannel_and_device_api(eng, port):
+    import torch
+
+    irsize, vsize, ch, nb = 256, 32, 5, 40
+    rng = np.random.default_rng(21)
+    ir = (rng.standard_normal((ch, irsize)) / 16).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, ch, vsize)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, ch, vsize)) / 16).astype(np.float32)
+    c = eng.Cldconv(0, irsize, vsize, channels=ch)
+    d = eng.Cldconv(0, irsize, vsize, channels=ch)
+    assert c.push_ir(ir) == 0
+    assert d.push_ir_dev(torch.from_numpy(ir).cuda(), irsize) == 0
+    y = np.zeros_like(x)
+    dx, dx2 = torch.from_numpy(x).cuda(), torch.from_numpy(x2).cuda()
+    dy = torch.zeros_like(dx)
+    for t in range(nb):
+        assert c.convolution(y[t], x[t], x2[t]) == 0
+        assert d.convolution_dev(dy[t], dx[t], dx2[t]) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(dy.cpu().numpy(), y)  # host and device entry points: same kernels, same bits
+    for k in range(ch):
+        o = port.dconv(irsize, vsize)
+        o.push_ir(ir[k])
+        want = np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])
+        assert rel_l2(y[:, k], want) < TOL
+    assert c.reset() == 0
+    y2 = np.zeros((ch, vsize), np.float32)
+    assert c.convolution(y2, x[0]) == 0
+    assert np.all(y2[:, 0] == 0)  # after reset the delay line is empty again (one-sample delay: first output is 0)
+
+
+def test_argument_errors(eng):
+    c = eng.Cldconv(0, 64, 16, channels=2, max_blocks=2)
+    x = np.zeros((2, 48), np.float32)
+    assert c.convolution(x.copy(), x, nblocks=3) == 6  # more blocks than max_blocks
+    assert eng.lib().b2f_dconv_process_host(None, None, None, 1) == 2
+    assert eng.Cldconv(0, 0, 16, errs=lambda s, d: None).get_cl_err() == 2

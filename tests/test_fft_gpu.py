@@ -201,3 +201,26 @@ def test_large_fft_every_transform_of_a_batch(eng, batch, cluster, monkeypatch):
         truth = np.fft.fft(zz, axis=1) / (size // 2) if fwd else np.fft.ifft(zz, axis=1) * (size // 2)
         err = np.linalg.norm(y - truth, axis=1) / np.linalg.norm(truth, axis=1)
         assert err.max() < 2e-6, (fwd, int(err.argmax()), float(err.max()))
+
+
+def test_empty_batch_and_null_arguments(eng):
+    p = eng.Clcfft(0, 64, True, max_batch=4)
+    L = eng.lib()
+    assert L.b2f_cfft_exec_host(p._h, np.zeros(64, np.complex64).ctypes.data, 0) == 0  # empty batch: nothing to do
+    assert L.b2f_cfft_exec_host(p._h, None, 1) == 2
+    assert L.b2f_cfft_exec_host(None, None, 1) == 2
+    assert L.b2f_cfft_exec_dev(p._h, None, None, 1, None) == 2
+    r = eng.Clrfft(0, 64, True)
+    assert L.b2f_rfft_exec_host(r._h, None, None, 1) == 2
+    assert eng.Clcfft(7, 64, True).get_error() == 1  # no such device
+
+
+def test_second_device_if_present(eng):
+    if eng.device_count() < 2:
+        pytest.skip("single-GPU box")
+    rng = np.random.default_rng(2)
+    x = crand(rng, 1024)
+    a, b = x.copy(), x.copy()
+    assert eng.Clcfft(0, 1024, True).transform(a) == 0
+    assert eng.Clcfft(1, 1024, True).transform(b) == 0
+    assert np.array_equal(a, b)

@@ -228,3 +228,16 @@ def test_large_partitions_general_path(eng, port, pts):
 def test_partition_size_limit(eng):
     c = eng.Clpconv(0, 1 << 18, 1 << 16, errs=lambda s, d: None)
     assert c.get_cl_err() == 3  # frames above 32768 complex points are not implemented
+
+
+def test_time_varying_multichannel(eng, port):
+    cvs, pts, ch, nb = 1024, 128, 6, 20  # 8 partitions, rings wrap twice
+    rng = np.random.default_rng(31)
+    x = rng.uniform(-1, 1, (nb, ch, pts)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, ch, pts)) * 0.1).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts, channels=ch)
+    y = run_stream(c, x, x2)
+    for k in (0, 3, 5):
+        o = port.pconv(cvs, pts)
+        want = np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])
+        assert rel_l2(y[:, k], want) < TOL
