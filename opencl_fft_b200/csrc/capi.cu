@@ -71,6 +71,31 @@ extern "C" int b2f_device_name(int device, char *buf, size_t buflen) {
   return B2F_OK;
 }
 
+// Make `device` current for the duration of an entry point and put the caller's device back afterwards: the
+// library must not change the calling thread's current device behind the application's (or torch's) back.
+struct DeviceGuard {
+  int prev = -1, rc = B2F_OK;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) {
+      cudaError_t e = cudaSetDevice(device);
+      if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        rc = B2F_ERR_NO_DEVICE;
+        prev = -1;
+      }
+    } else {
+      prev = -1;  // nothing to restore
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && cudaSetDevice(prev) != cudaSuccess) (void)cudaGetLastError();
+  }
+};
+#define B2F_ON_DEVICE(dev)       \
+  DeviceGuard device_guard_(dev); \
+  if (device_guard_.rc) return device_guard_.rc
+
 static int ilog2_exact(int n) {
   if (n <= 0 || (n & (n - 1))) return -1;
   int l = 0;
@@ -82,7 +107,6 @@ static int check_device(int device) {
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
   if (device < 0 || device >= n) return B2F_ERR_NO_DEVICE;
-  CK(cudaSetDevice(device));
   return B2F_OK;
 }
 
@@ -455,6 +479,7 @@ struct FftPlanCore {
     logn = ilog2_exact(n);
     int rc = check_device(dev);
     if (rc) return rc;
+    B2F_ON_DEVICE(dev);
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (is_large()) {
       rc = large.init(logn, max_batch);
@@ -487,7 +512,7 @@ struct FftPlanCore {
     return B2F_OK;
   }
   void destroy() {
-    if (cudaSetDevice(device) != cudaSuccess) (void)cudaGetLastError();  // never leave a stale error behind
+    DeviceGuard guard(device);  // a failed create may carry an invalid ordinal: the guard swallows that
     if (d_tw) cudaFree(d_tw);
     if (d_w2) cudaFree(d_w2);
     if (d_hw) cudaFree(d_hw);
@@ -547,7 +572,7 @@ extern "C" int b2f_cfft_exec_dev(b2f_cfft *plan, const void *d_in, void *d_out, 
   if (!plan || !d_in || !d_out || batch < 0) return B2F_ERR_INVALID_VALUE;
   if (batch == 0) return B2F_OK;
   FftPlanCore &c = plan->core;
-  CK(cudaSetDevice(c.device));
+  B2F_ON_DEVICE(c.device);
   return c.run_c2c((const float2 *)d_in, (float2 *)d_out, batch, (cudaStream_t)stream);
 }
 extern "C" int b2f_cfft_exec_host(b2f_cfft *plan, float *cdata, int batch) {
@@ -555,7 +580,7 @@ extern "C" int b2f_cfft_exec_host(b2f_cfft *plan, float *cdata, int batch) {
   if (batch == 0) return B2F_OK;
   FftPlanCore &c = plan->core;
   if (batch > c.max_batch) return B2F_ERR_BATCH;
-  CK(cudaSetDevice(c.device));
+  B2F_ON_DEVICE(c.device);
   int rc = c.ensure_buf();
   if (rc) return rc;
   const size_t bytes = (size_t)batch * c.N * sizeof(float2);
@@ -599,7 +624,7 @@ extern "C" int b2f_rfft_exec_dev(b2f_rfft *plan, const void *d_in, void *d_out, 
   if (!plan || !d_in || !d_out || batch < 0) return B2F_ERR_INVALID_VALUE;
   if (batch == 0) return B2F_OK;
   FftPlanCore &c = plan->core;
-  CK(cudaSetDevice(c.device));
+  B2F_ON_DEVICE(c.device);
   return c.run_real((const float2 *)d_in, (float2 *)d_out, batch, (cudaStream_t)stream);
 }
 extern "C" int b2f_rfft_exec_host(b2f_rfft *plan, float *cdata, float *r, int batch) {
@@ -607,7 +632,7 @@ extern "C" int b2f_rfft_exec_host(b2f_rfft *plan, float *cdata, float *r, int ba
   if (batch == 0) return B2F_OK;
   FftPlanCore &c = plan->core;
   if (batch > c.max_batch) return B2F_ERR_BATCH;
-  CK(cudaSetDevice(c.device));
+  B2F_ON_DEVICE(c.device);
   int rc = c.ensure_buf();
   if (rc) return rc;
   const size_t bytes = (size_t)batch * c.N * sizeof(float2);
@@ -647,7 +672,7 @@ struct b2f_pconv {
   bool general() const { return gfwd != nullptr; }
   size_t ring_elems() const { return (size_t)channels * nparts * pts; }
   void destroy() {
-    if (cudaSetDevice(device) != cudaSuccess) (void)cudaGetLastError();  // never leave a stale error behind
+    DeviceGuard guard(device);  // a failed create may carry an invalid ordinal: the guard swallows that
     for (void *p : {(void *)d_fdl, (void *)d_irs, (void *)d_tw, (void *)d_w2, (void *)d_tail, (void *)d_in1,
                     (void *)d_in2, (void *)d_out, (void *)d_ir, (void *)d_pad, (void *)d_Y})
       if (p) cudaFree(p);
@@ -746,6 +771,7 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   if (logp > 15 || channels > 65535) return B2F_ERR_UNSUPPORTED;  // frame = pts complex points <= 32768
   int rc = check_device(device);
   if (rc) return rc;
+  B2F_ON_DEVICE(device);
   b2f_pconv *h = new (std::nothrow) b2f_pconv;
   if (!h) return B2F_ERR_ALLOC;
   h->device = device, h->cvs = cvs, h->pts = pts, h->logp = logp, h->channels = channels;
@@ -805,7 +831,7 @@ extern "C" int b2f_pconv_nparts(const b2f_pconv *h) { return h ? h->nparts : 0; 
 
 extern "C" int b2f_pconv_reset(b2f_pconv *h) {
   if (!h) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   CK(cudaMemsetAsync(h->d_fdl, 0, h->ring_elems() * sizeof(float2), h->stream));
   CK(cudaMemsetAsync(h->d_tail, 0, (size_t)h->channels * h->pts * sizeof(float), h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -854,7 +880,7 @@ static int pconv_general_step(b2f_pconv *h, bool tv, float *d_out, const float *
 
 extern "C" int b2f_pconv_push_ir_dev(b2f_pconv *h, const void *d_ir, size_t ir_stride, void *stream) {
   if (!h || !d_ir || ir_stride < (size_t)h->nparts * h->pts) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   if (h->general()) return pconv_general_push(h, (const float *)d_ir, ir_stride, (cudaStream_t)stream);
   int rc = launch_pconv_push(h->logp, (const float *)d_ir, ir_stride, h, (cudaStream_t)stream);
   // after nparts decrements the write position is back where it started (cl_conv.cpp:385)
@@ -862,7 +888,7 @@ extern "C" int b2f_pconv_push_ir_dev(b2f_pconv *h, const void *d_ir, size_t ir_s
 }
 extern "C" int b2f_pconv_push_ir_host(b2f_pconv *h, const float *ir, size_t ir_stride) {
   if (!h || !ir || ir_stride < (size_t)h->nparts * h->pts) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   const size_t per = (size_t)h->nparts * h->pts;
   if (!h->d_ir) CK(cudaMalloc((void **)&h->d_ir, (size_t)h->channels * per * sizeof(float)));
   CK(cudaMemcpy2DAsync(h->d_ir, per * sizeof(float), ir, ir_stride * sizeof(float), per * sizeof(float), h->channels,
@@ -888,12 +914,12 @@ static int pconv_enqueue(b2f_pconv *h, bool tv, float *d_out, const float *d_in1
 }
 extern "C" int b2f_pconv_process_dev(b2f_pconv *h, void *d_out, const void *d_in, void *stream) {
   if (!h || !d_out || !d_in) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   return pconv_enqueue(h, false, (float *)d_out, (const float *)d_in, nullptr, (cudaStream_t)stream);
 }
 extern "C" int b2f_pconv_process_tv_dev(b2f_pconv *h, void *d_out, const void *d_in1, const void *d_in2, void *stream) {
   if (!h || !d_out || !d_in1 || !d_in2) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   return pconv_enqueue(h, true, (float *)d_out, (const float *)d_in1, (const float *)d_in2, (cudaStream_t)stream);
 }
 static int pconv_host_bufs(b2f_pconv *h, bool tv) {
@@ -905,7 +931,7 @@ static int pconv_host_bufs(b2f_pconv *h, bool tv) {
 }
 extern "C" int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in) {
   if (!h || !out || !in) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   int rc = pconv_host_bufs(h, false);
   if (rc) return rc;
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
@@ -923,7 +949,7 @@ extern "C" int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in)
 }
 extern "C" int b2f_pconv_process_tv_host(b2f_pconv *h, float *out, const float *in1, const float *in2) {
   if (!h || !out || !in1 || !in2) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   int rc = pconv_host_bufs(h, true);
   if (rc) return rc;
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
@@ -945,7 +971,7 @@ extern "C" int b2f_pconv_process_tv_host(b2f_pconv *h, float *out, const float *
 }
 extern "C" int b2f_pconv_read_spectra(b2f_pconv *h, int which, int channel, float *dst) {
   if (!h || !dst || channel < 0 || channel >= h->channels || (which != 1 && which != 2)) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   const size_t per = (size_t)h->nparts * h->pts;
   const float2 *src = (which == 1 ? h->d_fdl : h->d_irs) + (size_t)channel * per;
   CK(cudaStreamSynchronize(h->stream));
@@ -966,7 +992,7 @@ struct b2f_dconv {
   Staging sg_in, sg_in2, sg_out;
   int L() const { return irsize + vsize; }
   void destroy() {
-    if (cudaSetDevice(device) != cudaSuccess) (void)cudaGetLastError();  // never leave a stale error behind
+    DeviceGuard guard(device);  // a failed create may carry an invalid ordinal: the guard swallows that
     for (void *p : {(void *)d_hist[0], (void *)d_hist[1], (void *)d_coefs, (void *)d_grev, (void *)d_in1, (void *)d_in2,
                     (void *)d_out})
       if (p) cudaFree(p);
@@ -984,6 +1010,7 @@ extern "C" int b2f_dconv_create(b2f_dconv **out, int device, int irsize, int vsi
   if (channels > 65535) return B2F_ERR_UNSUPPORTED;
   int rc = check_device(device);
   if (rc) return rc;
+  B2F_ON_DEVICE(device);
   b2f_dconv *h = new (std::nothrow) b2f_dconv;
   if (!h) return B2F_ERR_ALLOC;
   h->device = device, h->irsize = irsize, h->vsize = vsize, h->channels = channels;
@@ -1016,7 +1043,7 @@ extern "C" int b2f_dconv_destroy(b2f_dconv *h) {
 }
 extern "C" int b2f_dconv_reset(b2f_dconv *h) {
   if (!h) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   for (int i = 0; i < 2; i++) CK(cudaMemsetAsync(h->d_hist[i], 0, (size_t)h->channels * h->irsize * sizeof(float), h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->wp = 0;
@@ -1031,14 +1058,14 @@ static int dconv_reverse(b2f_dconv *h, cudaStream_t st) {
 }
 extern "C" int b2f_dconv_push_ir_dev(b2f_dconv *h, const void *d_ir, size_t ir_stride, void *stream) {
   if (!h || !d_ir || ir_stride < (size_t)h->irsize) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   CK(cudaMemcpy2DAsync(h->d_coefs, (size_t)h->L() * sizeof(float), d_ir, ir_stride * sizeof(float),
                        (size_t)h->irsize * sizeof(float), h->channels, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return dconv_reverse(h, (cudaStream_t)stream);
 }
 extern "C" int b2f_dconv_push_ir_host(b2f_dconv *h, const float *ir, size_t ir_stride) {
   if (!h || !ir || ir_stride < (size_t)h->irsize) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   CK(cudaMemcpy2DAsync(h->d_coefs, (size_t)h->L() * sizeof(float), ir, ir_stride * sizeof(float),
                        (size_t)h->irsize * sizeof(float), h->channels, cudaMemcpyHostToDevice, h->stream));
   int rc = dconv_reverse(h, h->stream);
@@ -1088,7 +1115,7 @@ static int dconv_enqueue(b2f_dconv *h, float *d_out, const float *d_in, int nblo
 extern "C" int b2f_dconv_process_dev(b2f_dconv *h, void *d_out, const void *d_in, int nblocks, void *stream) {
   if (!h || !d_out || !d_in || nblocks < 1) return B2F_ERR_INVALID_VALUE;
   if (tiles_too_many((long long)nblocks * h->vsize)) return B2F_ERR_UNSUPPORTED;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   return dconv_enqueue(h, (float *)d_out, (const float *)d_in, nblocks, (cudaStream_t)stream);
 }
 static int dconv_coef_write(b2f_dconv *h, const float *d_in2, cudaStream_t st) {
@@ -1099,7 +1126,7 @@ static int dconv_coef_write(b2f_dconv *h, const float *d_in2, cudaStream_t st) {
 }
 extern "C" int b2f_dconv_process_tv_dev(b2f_dconv *h, void *d_out, const void *d_in1, const void *d_in2, void *stream) {
   if (!h || !d_out || !d_in1 || !d_in2) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   int rc = dconv_coef_write(h, (const float *)d_in2, (cudaStream_t)stream);
   if (rc) return rc;
   return dconv_enqueue(h, (float *)d_out, (const float *)d_in1, 1, (cudaStream_t)stream);
@@ -1114,7 +1141,7 @@ static int dconv_host_bufs(b2f_dconv *h, bool tv) {
 extern "C" int b2f_dconv_process_host(b2f_dconv *h, float *out, const float *in, int nblocks) {
   if (!h || !out || !in || nblocks < 1) return B2F_ERR_INVALID_VALUE;
   if (nblocks > h->max_blocks) return B2F_ERR_BATCH;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   int rc = dconv_host_bufs(h, false);
   if (rc) return rc;
   const size_t bytes = (size_t)h->channels * nblocks * h->vsize * sizeof(float);
@@ -1132,7 +1159,7 @@ extern "C" int b2f_dconv_process_host(b2f_dconv *h, float *out, const float *in,
 }
 extern "C" int b2f_dconv_process_tv_host(b2f_dconv *h, float *out, const float *in1, const float *in2) {
   if (!h || !out || !in1 || !in2) return B2F_ERR_INVALID_VALUE;
-  CK(cudaSetDevice(h->device));
+  B2F_ON_DEVICE(h->device);
   int rc = dconv_host_bufs(h, true);
   if (rc) return rc;
   const size_t bytes = (size_t)h->channels * h->vsize * sizeof(float);
