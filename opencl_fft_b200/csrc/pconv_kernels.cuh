@@ -25,6 +25,39 @@ namespace b2f {
 
 namespace cg = cooperative_groups;
 
+// ---- PTX helpers for the TMA-fed pipelines: bulk global->shared copies completed on mbarriers ---------------
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TMA_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TMA_WAIT_DONE;\n"
+      "bra TMA_WAIT_LOOP;\n"
+      "TMA_WAIT_DONE:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+}  // namespace tma
+
 constexpr int kPconvMaxLogP = 12;  // fused path: pts <= 4096 (shared-memory budget incl. time-varying)
 
 template <int LOGP>
@@ -39,6 +72,10 @@ struct PconvGeom {
   static constexpr int NTHREADS = THREADS > FT ? THREADS : FT;
   static constexpr int TILES = (HALF + NTHREADS - 1) / NTHREADS;
   static constexpr int FFT_SMEM = VT * G::SMEM;            // float2 entries per FFT work buffer
+  // TMA-fed MAC: one extra (producer) warp, a ring of STAGES x {FDL slice, IR slice} of SLICE float4 each
+  static constexpr int STAGES = 6;
+  static constexpr int SLICE = HALF < NTHREADS ? HALF : NTHREADS;  // float4 per slice (16 B .. 4 KB)
+  static constexpr int RING_F4 = 2 * STAGES * SLICE;
 };
 
 // barrier over the FFT participants only (warps 0 .. FT/32-1); id 1, the CTA barrier is id 0
@@ -68,7 +105,7 @@ __device__ __forceinline__ void pconv_forward_frame(const float *x, float2 *sm, 
     fft_run<LOGP, false, true>(load, store, my, tw, t, FftGroupSync<P::FT>());
   }
   __syncthreads();
-  for (int i = tid; i < N / 2; i += P::NTHREADS) {
+  for (int i = tid; i < N / 2 && tid < P::NTHREADS; i += P::NTHREADS) {  // (a TMA producer warp only syncs)
     if (i == 0) {
       sm[pad_idx(0)] = rfft_dc<false>(sm[pad_idx(0)]);
     } else {
@@ -135,14 +172,32 @@ struct PconvArgs {
 // grid = (S, channels), cluster = (S,1,1). Rank r of a cluster handles partitions
 // [r*nparts/S, (r+1)*nparts/S) minus the frames written in this very launch, which rank 0 takes
 // from its shared memory instead.
-template <int LOGP, bool TV>
-__global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS) pconv_step_kernel(PconvArgs a) {
+// TMA: the partitions are streamed by the TMA engine (cp.async.bulk, one producer warp, an mbarrier ring in
+// shared memory) instead of 128-bit loads into registers; block = NTHREADS + 32.
+template <int LOGP, bool TV, bool TMA>
+__global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pconv_step_kernel(PconvArgs a) {
   using P = PconvGeom<LOGP>;
   constexpr int PTS = P::PTS, HALF = P::HALF, NT = P::NTHREADS;
   extern __shared__ float4 smem4[];
   float2 *sX = reinterpret_cast<float2 *>(smem4);         // new input spectrum, later Y / IFFT buffer
   float2 *sG = sX + P::FFT_SMEM + (P::FFT_SMEM & 1);      // new IR spectrum (TV only)
   float4 *sP = reinterpret_cast<float4 *>(sG + (TV ? P::FFT_SMEM + (P::FFT_SMEM & 1) : 0));  // partials [HALF]
+  float4 *ring = sP + (P::TILES > 1 ? 2 : 1) * HALF;      // TMA ring: [STAGES][2][SLICE] float4, then barriers
+  const bool worker = !TMA || threadIdx.x < NT;           // false only for the producer warp
+  uint32_t bar_full = 0, bar_empty = 0, slot = 0;         // slot: running ring position, identical in all threads
+  if (TMA) {
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + P::RING_F4);
+    bar_full = tma::smem_u32(bars);
+    bar_empty = tma::smem_u32(bars + P::STAGES);
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < P::STAGES; s++) {
+        tma::mbar_init(bar_full + 8 * s, 1);         // the producer's expect_tx arrive + the bytes
+        tma::mbar_init(bar_empty + 8 * s, NT / 32);  // one arrive per consumer warp
+      }
+      tma::fence_barrier_init();
+    }
+    __syncthreads();
+  }
 
   cg::cluster_group cluster = cg::this_cluster();
   const int S = (int)cluster.num_blocks();
@@ -160,10 +215,10 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS) pconv_step_kernel(P
     if (TV) pconv_forward_frame<LOGP>(a.in2 + (size_t)ch * PTS, sG, a.tw, a.w2);
     // store the new frames for future blocks (this launch never reads them back from HBM)
     float2 *fx = fdl + (size_t)a.wp * PTS;
-    for (int i = tid; i < PTS; i += NT) fx[i] = sX[pad_idx(i)];
+    for (int i = tid; i < PTS && worker; i += NT) fx[i] = sX[pad_idx(i)];
     if (TV) {
       float2 *gx = irs + (size_t)a.wp2 * PTS;
-      for (int i = tid; i < PTS; i += NT) gx[i] = sG[pad_idx(i)];
+      for (int i = tid; i < PTS && worker; i += NT) gx[i] = sG[pad_idx(i)];
     }
   }
 
@@ -189,14 +244,47 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS) pconv_step_kernel(P
 
   for (int tile = 0; tile < P::TILES; tile++) {
     const int q = tile * NT + tid;  // float4 index inside a frame: bins 2q, 2q+1
-    const bool owns = q < HALF;
+    const bool owns = worker && q < HALF;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float2 acc0 = make_float2(0.f, 0.f);
+    if (TMA) {
+      // every thread walks the same sequence of partitions (ascending p, the frames written by this launch
+      // left out), so `slot` advances identically in the producer and in the consumers
+      constexpr uint32_t kSliceBytes = P::SLICE * (uint32_t)sizeof(float4);
+      const unsigned char *Fb = reinterpret_cast<const unsigned char *>(reinterpret_cast<const float4 *>(fdl) + tile * NT);
+      const unsigned char *Gb = reinterpret_cast<const unsigned char *>(reinterpret_cast<const float4 *>(irs) + tile * NT);
+      const size_t frame_bytes = (size_t)PTS * sizeof(float2);
+      for (int p = p_lo; p < p_hi; p++) {
+        if (p == p_newx || p == p_newg) continue;
+        const uint32_t s = slot % P::STAGES, round = slot / P::STAGES;
+        slot++;
+        if (!worker) {
+          if ((tid & 31) == 0) {
+            if (round > 0) tma::mbar_wait(bar_empty + 8 * s, (round - 1) & 1);  // consumers released the stage
+            const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
+            tma::mbar_expect_tx(bar_full + 8 * s, 2 * kSliceBytes);
+            tma::bulk_g2s(tma::smem_u32(ring + (2 * s) * P::SLICE), Fb + (size_t)frame * frame_bytes, kSliceBytes, bar_full + 8 * s);
+            tma::bulk_g2s(tma::smem_u32(ring + (2 * s + 1) * P::SLICE), Gb + (size_t)p * frame_bytes, kSliceBytes, bar_full + 8 * s);
+          }
+        } else {
+          tma::mbar_wait(bar_full + 8 * s, round & 1);
+          if (owns) {
+            const float4 fa = ring[(2 * s) * P::SLICE + tid], gb = ring[(2 * s + 1) * P::SLICE + tid];
+            cmac2(acc, fa, gb);
+            acc0.x += fa.x * gb.x;
+            acc0.y += fa.y * gb.y;
+          }
+          __syncwarp();
+          if ((tid & 31) == 0) tma::mbar_arrive(bar_empty + 8 * s);
+        }
+      }
+      __syncwarp();  // the producer warp's lane 0 rejoins its warp before the next (aligned) barrier
+    }
     if (owns) {
       const float4 *F = reinterpret_cast<const float4 *>(fdl) + q;
       const float4 *Gp = reinterpret_cast<const float4 *>(irs) + q;
       // walk [p_lo, p_hi) in ascending p, cutting at the FDL wrap point and around the new frames
-      int p = p_lo;
+      int p = TMA ? p_hi : p_lo;
       while (p < p_hi) {
         if (p == p_newx || p == p_newg) {
           p++;
@@ -273,7 +361,7 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS) pconv_step_kernel(P
   if (rank != 0) return;
   __syncthreads();
   if (P::TILES > 1) {
-    for (int q = tid; q < HALF; q += NT) {
+    for (int q = tid; q < HALF && worker; q += NT) {
       float4 y = sP[HALF + q];
       sX[pad_idx(2 * q)] = make_float2(y.x, y.y);
       sX[pad_idx(2 * q + 1)] = make_float2(y.z, y.w);
@@ -282,7 +370,7 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS) pconv_step_kernel(P
   }
 
   // ---- 3. unsplit (cl_conv_kernels.h:87-100), inverse FFT, overlap-add (120-124) ------------------
-  for (int i = tid; i < PTS / 2; i += NT) {
+  for (int i = tid; i < PTS / 2 && worker; i += NT) {
     if (i == 0) {
       sX[pad_idx(0)] = rfft_dc<true>(sX[pad_idx(0)]);
     } else {
@@ -306,7 +394,7 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS) pconv_step_kernel(P
   const float inv = 1.0f / (float)PTS;
   float2 *out2 = reinterpret_cast<float2 *>(a.out + (size_t)ch * PTS);
   float2 *tail2 = reinterpret_cast<float2 *>(a.tail + (size_t)ch * PTS);
-  for (int m = tid; m < PTS / 2; m += NT) {
+  for (int m = tid; m < PTS / 2 && worker; m += NT) {
     float2 y = sX[pad_idx(m)], z = sX[pad_idx(m + PTS / 2)], tl = tail2[m];
     out2[m] = make_float2((y.x + tl.x) * inv, (y.y + tl.y) * inv);
     tail2[m] = z;
@@ -367,6 +455,73 @@ __global__ void __launch_bounds__(256)
     acc.y = acc0.y;
   }
   reinterpret_cast<float4 *>(Y)[(size_t)ch * stride4 + q] = acc;
+}
+
+// ---- the same MAC fed by the TMA engine -----------------------------------------------------------------------
+// One producer thread issues `cp.async.bulk` copies (UBLKCP: global -> shared, completion counted on an mbarrier)
+// of the 4 KB FDL slice and the 4 KB IR slice of partition p into an 8-stage ring; the 8 consumer warps wait on
+// the stage's "full" barrier, multiply-accumulate out of shared memory and release the stage through its "empty"
+// barrier. No registers are tied up by loads in flight (64 KB per CTA sits in the ring), address generation is
+// off the SM's issue slots.
+
+constexpr int kMacStages = 8;
+constexpr int kMacTileBins = 512;                                  // bins per CTA: 4 KB per frame slice
+constexpr int kMacSliceBytes = kMacTileBins * (int)sizeof(float2);
+constexpr int kMacTmaSmem = kMacStages * 2 * kMacSliceBytes + 1024;  // ring + barriers (+ alignment slack)
+
+// grid = (pts / 512, channels), 288 threads: warps 0-7 consume, warp 8 lane 0 produces.
+__global__ void __launch_bounds__(288)
+    pconv_mac_tma_kernel(const float2 *fdl, const float2 *irs, float2 *Y, int pts, int nparts, int rp) {
+  extern __shared__ __align__(128) unsigned char mac_smem[];
+  float4 *ringF = reinterpret_cast<float4 *>(mac_smem);
+  float4 *ringG = reinterpret_cast<float4 *>(mac_smem + kMacStages * kMacSliceBytes);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(mac_smem + 2 * kMacStages * kMacSliceBytes);
+  const uint32_t full0 = tma::smem_u32(bars), empty0 = tma::smem_u32(bars + kMacStages);
+  const int ch = blockIdx.y, tile = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const size_t frame_bytes = (size_t)pts * sizeof(float2);
+  const unsigned char *Fb = reinterpret_cast<const unsigned char *>(fdl) + (size_t)ch * nparts * frame_bytes +
+                            (size_t)tile * kMacSliceBytes;
+  const unsigned char *Gb = reinterpret_cast<const unsigned char *>(irs) + (size_t)ch * nparts * frame_bytes +
+                            (size_t)tile * kMacSliceBytes;
+  if (tid == 0) {
+    for (int s = 0; s < kMacStages; s++) {
+      tma::mbar_init(full0 + 8 * s, 1);   // one arrive (the producer's expect_tx) + the bytes
+      tma::mbar_init(empty0 + 8 * s, 8);  // one arrive per consumer warp
+    }
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    if ((tid & 31) == 0) {
+      for (int p = 0; p < nparts; p++) {
+        const int s = p % kMacStages, round = p / kMacStages;
+        if (round > 0) tma::mbar_wait(empty0 + 8 * s, (round - 1) & 1);  // consumers released the stage
+        const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
+        tma::mbar_expect_tx(full0 + 8 * s, 2 * kMacSliceBytes);
+        tma::bulk_g2s(tma::smem_u32(ringF) + s * kMacSliceBytes, Fb + (size_t)frame * frame_bytes, kMacSliceBytes, full0 + 8 * s);
+        tma::bulk_g2s(tma::smem_u32(ringG) + s * kMacSliceBytes, Gb + (size_t)p * frame_bytes, kMacSliceBytes, full0 + 8 * s);
+      }
+    }
+    return;
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 acc0 = make_float2(0.f, 0.f);
+  for (int p = 0; p < nparts; p++) {
+    const int s = p % kMacStages, round = p / kMacStages;
+    tma::mbar_wait(full0 + 8 * s, round & 1);
+    const float4 a = ringF[s * (kMacSliceBytes / 16) + tid], b = ringG[s * (kMacSliceBytes / 16) + tid];
+    cmac2(acc, a, b);
+    acc0.x += a.x * b.x;
+    acc0.y += a.y * b.y;
+    __syncwarp();
+    if ((tid & 31) == 0) tma::mbar_arrive(empty0 + 8 * s);
+  }
+  if (tile == 0 && tid == 0) {  // packed (DC, Nyquist) bin: component-wise product
+    acc.x = acc0.x;
+    acc.y = acc0.y;
+  }
+  reinterpret_cast<float4 *>(Y)[(size_t)ch * (pts / 2) + (size_t)tile * 256 + tid] = acc;
 }
 
 // y [channels][2*pts] (inverse transform, unnormalised) -> out = (y[0,pts) + tail) / pts, tail = y[pts, 2pts)

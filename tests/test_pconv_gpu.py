@@ -241,3 +241,29 @@ def test_time_varying_multichannel(eng, port):
         o = port.pconv(cvs, pts)
         want = np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])
         assert rel_l2(y[:, k], want) < TOL
+
+
+@pytest.mark.parametrize("tma", ["0", "1"])
+@pytest.mark.parametrize("pts,channels", [(64, 3), (512, 70), (1024, 70), (2048, 2), (8192, 2)])
+def test_both_mac_feeds(eng, port, monkeypatch, tma, pts, channels):
+    """The spectral multiply-accumulate exists twice: fed by 128-bit register loads and fed by the TMA engine
+    (cp.async.bulk into an mbarrier ring). The library picks by shape; B2F_PCONV_TMA forces either. Both must
+    match the oracle, static and time-varying, including ring wrap."""
+    monkeypatch.setenv("B2F_PCONV_TMA", tma)  # read at the first launch of each kernel family
+    nparts = 5
+    cvs, nb = nparts * pts, 2 * nparts + 2
+    rng = np.random.default_rng(pts + channels)
+    ir = (rng.standard_normal((channels, cvs)) * 0.1).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, channels, pts)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, channels, pts)) * 0.1).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts, channels=channels)
+    assert c.push_ir(ir) == 0
+    y = run_stream(c, x)
+    ctv = eng.Clpconv(0, cvs, pts, channels=channels)
+    ytv = run_stream(ctv, x, x2)
+    for k in sorted({0, channels - 1}):
+        o = port.pconv(cvs, pts)
+        o.push_ir(ir[k])
+        assert rel_l2(y[:, k], np.stack([o.convolution(x[t, k]) for t in range(nb)])) < TOL
+        o = port.pconv(cvs, pts)
+        assert rel_l2(ytv[:, k], np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])) < TOL
