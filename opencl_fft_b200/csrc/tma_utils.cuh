@@ -1,0 +1,42 @@
+// tma_utils.cuh -- inline-PTX helpers for TMA-fed pipelines: 1-D bulk global->shared copies (cp.async.bulk, SASS
+// UBLKCP) whose completion is counted on shared-memory mbarriers. Used by the partitioned-convolution MAC
+// (pconv_kernels.cuh) and by the rows kernel of the large FFT (fft_large.cuh).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b2f {
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TMA_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TMA_WAIT_DONE;\n"
+      "bra TMA_WAIT_LOOP;\n"
+      "TMA_WAIT_DONE:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+}  // namespace tma
+
+}  // namespace b2f
