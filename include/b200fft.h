@@ -21,6 +21,9 @@
  *     is in the caller's buffer), like the reference's blocking reads (cl_fft.cpp:158).
  *   - "dev" entry points take device pointers and a cudaStream_t (passed as void*) and only
  *     enqueue work; this is the batched, HBM-resident path the roofline numbers are measured on.
+ *     FFT and partitioned-convolution block pointers must be 16-byte aligned (B2F_ERR_INVALID_VALUE
+ *     otherwise); impulse responses and direct-convolution blocks need only float alignment, and
+ *     `ir_stride` may be any value >= the IR length.
  *   - complex data is interleaved float32 (re, im) == std::complex<float> == OpenCL float2.
  *   - batch / channels: the reference has one object per transform / channel; a handle here
  *     carries `max_batch` transforms or `channels` independent convolver states and runs them in

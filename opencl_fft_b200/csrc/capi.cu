@@ -96,6 +96,9 @@ struct DeviceGuard {
   DeviceGuard device_guard_(dev); \
   if (device_guard_.rc) return device_guard_.rc
 
+// device-pointer entry points use 64/128-bit accesses: base pointers must be 16-byte aligned (include/b200fft.h)
+static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 static int ilog2_exact(int n) {
   if (n <= 0 || (n & (n - 1))) return -1;
   int l = 0;
@@ -569,7 +572,7 @@ extern "C" int b2f_cfft_destroy(b2f_cfft *plan) {
   return B2F_OK;
 }
 extern "C" int b2f_cfft_exec_dev(b2f_cfft *plan, const void *d_in, void *d_out, int batch, void *stream) {
-  if (!plan || !d_in || !d_out || batch < 0) return B2F_ERR_INVALID_VALUE;
+  if (!plan || !d_in || !d_out || batch < 0 || !al16(d_in) || !al16(d_out)) return B2F_ERR_INVALID_VALUE;
   if (batch == 0) return B2F_OK;
   FftPlanCore &c = plan->core;
   B2F_ON_DEVICE(c.device);
@@ -621,7 +624,7 @@ extern "C" int b2f_rfft_destroy(b2f_rfft *plan) {
   return B2F_OK;
 }
 extern "C" int b2f_rfft_exec_dev(b2f_rfft *plan, const void *d_in, void *d_out, int batch, void *stream) {
-  if (!plan || !d_in || !d_out || batch < 0) return B2F_ERR_INVALID_VALUE;
+  if (!plan || !d_in || !d_out || batch < 0 || !al16(d_in) || !al16(d_out)) return B2F_ERR_INVALID_VALUE;
   if (batch == 0) return B2F_OK;
   FftPlanCore &c = plan->core;
   B2F_ON_DEVICE(c.device);
@@ -935,12 +938,12 @@ static int pconv_enqueue(b2f_pconv *h, bool tv, float *d_out, const float *d_in1
   return B2F_OK;
 }
 extern "C" int b2f_pconv_process_dev(b2f_pconv *h, void *d_out, const void *d_in, void *stream) {
-  if (!h || !d_out || !d_in) return B2F_ERR_INVALID_VALUE;
+  if (!h || !d_out || !d_in || !al16(d_out) || !al16(d_in)) return B2F_ERR_INVALID_VALUE;
   B2F_ON_DEVICE(h->device);
   return pconv_enqueue(h, false, (float *)d_out, (const float *)d_in, nullptr, (cudaStream_t)stream);
 }
 extern "C" int b2f_pconv_process_tv_dev(b2f_pconv *h, void *d_out, const void *d_in1, const void *d_in2, void *stream) {
-  if (!h || !d_out || !d_in1 || !d_in2) return B2F_ERR_INVALID_VALUE;
+  if (!h || !d_out || !d_in1 || !d_in2 || !al16(d_out) || !al16(d_in1) || !al16(d_in2)) return B2F_ERR_INVALID_VALUE;
   B2F_ON_DEVICE(h->device);
   return pconv_enqueue(h, true, (float *)d_out, (const float *)d_in1, (const float *)d_in2, (cudaStream_t)stream);
 }

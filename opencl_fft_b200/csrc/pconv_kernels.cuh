@@ -66,8 +66,11 @@ __device__ __forceinline__ void pconv_forward_frame(const float *x, float2 *sm, 
     const int vt = tid / P::T, t = tid % P::T;
     float2 *my = sm + vt * FftGeom<LOGP>::SMEM;
     const bool real = (vt == 0);
+    // an IR pushed with an odd channel stride (push_ir_dev) leaves rows that are only 4-byte aligned
+    const bool pair_ok = (reinterpret_cast<uintptr_t>(x) & 7) == 0;
     auto load = [&](int idx, int) {
-      if (real && idx < N / 2) return *reinterpret_cast<const float2 *>(x + 2 * idx);
+      if (real && idx < N / 2)
+        return pair_ok ? *reinterpret_cast<const float2 *>(x + 2 * idx) : make_float2(x[2 * idx], x[2 * idx + 1]);
       return make_float2(0.f, 0.f);
     };
     auto store = [&](int idx, float2 v, int) { my[pad_idx(idx)] = v; };

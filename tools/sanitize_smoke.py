@@ -1,0 +1,63 @@
+"""Small invocation of every kernel family, for compute-sanitizer (memcheck / racecheck, one tool per run):
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+Sizes are kept tiny: the tools slow kernels down 10-100x."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import opencl_fft_b200 as eng  # noqa: E402
+
+rng = np.random.default_rng(0)
+
+
+def crand(*shape):
+    return (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(np.complex64)
+
+
+# batched FFTs of every schedule class (single pass, 2, 3, 4 passes), forward and inverse, real and complex
+for n, batch in ((16, 5), (64, 5), (512, 3), (1024, 3), (4096, 2), (8192, 1)):
+    x = crand(batch, n)
+    for fwd in (True, False):
+        p = eng.Clcfft(0, n, fwd, max_batch=batch)
+        y = x.copy()
+        assert p.transform(y.reshape(-1)) == 0
+    r = rng.uniform(-1, 1, (batch, 2 * n)).astype(np.float32)
+    c = np.zeros((batch, n), np.complex64)
+    assert eng.Clrfft(0, 2 * n, True, max_batch=batch).transform(c.reshape(-1), r.reshape(-1)) == 0
+    assert eng.Clrfft(0, 2 * n, False, max_batch=batch).transform(c.reshape(-1), r.reshape(-1)) == 0
+# large path (two kernels, fused split) and the opt-in cluster kernel
+for env in (None, "1"):
+    if env:
+        os.environ["B2F_CLUSTER_FFT"] = env
+    x = crand(3, 32768)
+    assert eng.Clcfft(0, 32768, True, max_batch=3).transform(x.reshape(-1)) == 0
+    r = rng.uniform(-1, 1, (3, 65536)).astype(np.float32)
+    c = np.zeros((3, 32768), np.complex64)
+    assert eng.Clrfft(0, 65536, True, max_batch=3).transform(c.reshape(-1), r.reshape(-1)) == 0
+    assert eng.Clrfft(0, 65536, False, max_batch=3).transform(c.reshape(-1), r.reshape(-1)) == 0
+os.environ.pop("B2F_CLUSTER_FFT", None)
+# partitioned convolution: fused kernel (1 CTA, clusters of 2..8, register- and TMA-fed), general path, time-varying
+for tma in ("0", "1"):
+    os.environ["B2F_PCONV_TMA"] = tma
+    for pts, nparts, ch in ((64, 5, 1), (512, 9, 3), (512, 5, 200), (1024, 4, 70), (8192, 3, 2)):
+        cvs = pts * nparts
+        c = eng.Clpconv(0, cvs, pts, channels=ch)
+        assert c.push_ir((rng.standard_normal((ch, cvs)) * 0.1).astype(np.float32)) == 0
+        y = np.zeros((ch, pts), np.float32)
+        for t in range(nparts + 2):
+            x = rng.uniform(-1, 1, (ch, pts)).astype(np.float32)
+            assert c.convolution(y, x) == 0
+            assert c.convolution(y, x, x * 0.1) == 0
+os.environ.pop("B2F_PCONV_TMA", None)
+# direct convolution: single block (cluster tap split), multi-block (16 outputs per thread), ragged sizes, time-varying
+for irsize, vsize, ch, nb in ((4096, 256, 2, 1), (4096, 256, 2, 6), (100, 16, 3, 1), (64, 1, 2, 3)):
+    d = eng.Cldconv(0, irsize, vsize, channels=ch, max_blocks=nb)
+    assert d.push_ir((rng.standard_normal((ch, irsize)) / 8).astype(np.float32)) == 0
+    x = rng.uniform(-1, 1, (ch, nb * vsize)).astype(np.float32)
+    y = np.zeros_like(x)
+    assert d.convolution(y, x, nblocks=nb) == 0
+    if nb == 1:
+        assert d.convolution(y, x, x * 0.1) == 0
+print("sanitize smoke done")
