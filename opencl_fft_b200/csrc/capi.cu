@@ -338,13 +338,13 @@ struct LargePlan {
     chunk = (int)(kScratchBytes / ((size_t)N * sizeof(float2)));
     if (chunk < 1) chunk = 1;
     if (chunk > max_batch) chunk = max_batch < 1 ? 1 : max_batch;
-    CK(cudaMalloc((void **)&d_scratch, (size_t)chunk * N * sizeof(float2)));
+    if (!fused_wanted()) CK(cudaMalloc((void **)&d_scratch, (size_t)chunk * N * sizeof(float2)));
     return B2F_OK;
   }
   void destroy() {
-    for (void *p : {(void *)d_tw1, (void *)d_tw2, (void *)d_twl, (void *)d_scratch})
+    for (void *p : {(void *)d_tw1, (void *)d_tw2, (void *)d_twl, (void *)d_scratch, (void *)d_fscratch})
       if (p) cudaFree(p);
-    d_tw1 = d_tw2 = d_twl = d_scratch = nullptr;
+    d_tw1 = d_tw2 = d_twl = d_scratch = d_fscratch = nullptr;
   }
   template <int L1, int L2, bool INV, bool REAL = false>
   int run_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw = nullptr) {
@@ -367,7 +367,59 @@ struct LargePlan {
     }
     return B2F_OK;
   }
+  // Both steps in one launch on 8-CTA clusters with cluster-private, L2-resident scratch (fft_large.cuh,
+  // large_fused_kernel): N = 2^15 only (8 column groups == 8 row groups == the portable cluster size).
+  // B2F_LARGE_TWO_KERNEL=1 selects the two-launch path instead.
+  float2 *d_fscratch = nullptr;
+  int fused_clusters = 0;
+  bool fused_wanted() const { return logn == 15 && getenv("B2F_LARGE_FUSED") && !getenv("B2F_LARGE_TWO_KERNEL"); }
+  template <int L1, int L2, bool INV, bool REAL, int MINB>
+  int run_fused_tt(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw) {
+    using L = LargeGeom<L1, L2>;
+    auto kern = large_fused_kernel<L1, L2, INV, REAL, MINB>;
+    const int smem = FusedGeom<L1, L2>::SMEM_BYTES;
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(L::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 8;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (fused_clusters == 0) {
+      cfg.gridDim = dim3(8 * 64, 1, 1);
+      int n = 0;
+      CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      if (getenv("B2F_VERBOSE")) fprintf(stderr, "b200fft: fused large FFT, %d resident 8-CTA clusters\n", n);
+      if (const char *e = getenv("B2F_FUSED_CLUSTERS")) n = atoi(e) > 0 ? atoi(e) : n;
+      fused_clusters = n > 0 ? n : 1;
+      CK(cudaMalloc((void **)&d_fscratch, (size_t)fused_clusters * FusedGeom<L1, L2>::NBUF * L::N * sizeof(float2)));
+    }
+    const int ncl = batch < fused_clusters ? batch : fused_clusters;
+    cfg.gridDim = dim3(8 * ncl, 1, 1);
+    static const int dbg = getenv("B2F_FUSED_DBG") ? atoi(getenv("B2F_FUSED_DBG")) : 0;  // timing experiments only
+    CK(cudaLaunchKernelEx(&cfg, kern, in, out, d_fscratch, (const float2 *)d_tw1, (const float2 *)d_tw2,
+                          (const float2 *)d_twl, hw, batch, scale, dbg));
+    return B2F_OK;
+  }
+  template <int L1, int L2, bool INV, bool REAL>
+  int run_fused_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw) {
+    static const int minb = [] {
+      const char *e = getenv("B2F_FUSED_MINB");
+      return e ? atoi(e) : 2;
+    }();
+    return minb >= 3 ? run_fused_tt<L1, L2, INV, REAL, 3>(in, out, batch, scale, st, hw)
+                     : run_fused_tt<L1, L2, INV, REAL, 2>(in, out, batch, scale, st, hw);
+  }
   int run_c2c(bool inv, const float2 *in, float2 *out, int batch, float scale, cudaStream_t st) {
+    if (fused_wanted())
+      return inv ? run_fused_t<7, 8, true, false>(in, out, batch, scale, st, nullptr)
+                 : run_fused_t<7, 8, false, false>(in, out, batch, scale, st, nullptr);
     if (logn == 15) return inv ? run_t<7, 8, true>(in, out, batch, scale, st) : run_t<7, 8, false>(in, out, batch, scale, st);
     if (logn == 16) return inv ? run_t<8, 8, true>(in, out, batch, scale, st) : run_t<8, 8, false>(in, out, batch, scale, st);
     return B2F_ERR_UNSUPPORTED;
@@ -376,6 +428,7 @@ struct LargePlan {
                cudaStream_t st) {
     const int N = 1 << logn;
     if (!inv && !getenv("B2F_SEPARATE_SPLIT")) {  // forward: split fused into the rows kernel
+      if (fused_wanted()) return run_fused_t<7, 8, false, true>(in, out, batch, fwd_scale, st, hw);
       if (logn == 15) return run_t<7, 8, false, true>(in, out, batch, fwd_scale, st, hw);
       if (logn == 16) return run_t<8, 8, false, true>(in, out, batch, fwd_scale, st, hw);
     }

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(ClusterGeom<LOG1, CLUSTER>::THREADS, ClusterGe
       else
         v[j] = cluster.map_shared_rank(sA, j / C::COLS)[off];
     }
-    v[0] = make_float2(v[0].x * scale, v[0].y * scale);
+    v[0] = cscale(v[0], scale);
 #pragma unroll
     for (int j = 1; j < 16; j++) v[j] = cmul(v[j], tw3[j]);
     B2F_PROBE(2);

@@ -22,13 +22,69 @@
 
 namespace b2f {
 
+// ---- complex arithmetic on Blackwell's packed-FP32 instructions -------------------------------------------
+// sm_100a has two-lane FP32 instructions on 64-bit register pairs (PTX add/sub/mul/fma.rn.f32x2 -> SASS FADD2 /
+// FMUL2 / FFMA2). An interleaved complex value IS such a pair, and the SASS operands take free modifiers -- lane
+// swap (.LO_HI), per-lane negate (.NP), scalar broadcast (.F32) -- which ptxas folds from the mov.b64 pack /
+// unpack below. So a complex add is ONE instruction, a quarter turn folded into the following add costs none, a
+// complex multiply is two (FMUL2 + FFMA2). The FP32 pipe spends the same cycles as with scalar code (FFMA2 issues
+// every other cycle per scheduler, tools/pk_probe.cu), but the instruction count of a radix-16 pass halves,
+// which is what large transforms are bound by. -DB2F_PACKED=0 builds the scalar forms.
+#ifndef B2F_PACKED
+#define B2F_PACKED 1
+#endif
+typedef unsigned long long b2f_u64;
+__device__ __forceinline__ b2f_u64 pk2(float lo, float hi) {
+  b2f_u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 up2(b2f_u64 v) {
+  float2 f;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v));
+  return f;
+}
+__device__ __forceinline__ b2f_u64 add2(b2f_u64 a, b2f_u64 b) {
+  b2f_u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ b2f_u64 sub2(b2f_u64 a, b2f_u64 b) {
+  b2f_u64 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ b2f_u64 mul2(b2f_u64 a, b2f_u64 b) {
+  b2f_u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ b2f_u64 fma2(b2f_u64 a, b2f_u64 b, b2f_u64 c) {
+  b2f_u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+#if B2F_PACKED
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return up2(add2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return up2(sub2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+// a * b = b.x * (a.x, a.y) + b.y * (-a.y, a.x)
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  const float2 t = up2(mul2(pk2(b.y, b.y), pk2(a.y, a.x)));
+  return up2(fma2(pk2(b.x, b.x), pk2(a.x, a.y), pk2(-t.x, t.y)));
+}
+// s * a for a real s
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return up2(mul2(pk2(a.x, a.y), pk2(s, s))); }
+#else
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+#endif
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-// multiply by -i (forward quarter turn) or +i (inverse)
+// multiply by -i (forward quarter turn) or +i (inverse); a lane swap + negate the next packed add absorbs
 template <bool INV>
 __device__ __forceinline__ float2 cquarter(float2 a) {
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
@@ -36,7 +92,12 @@ __device__ __forceinline__ float2 cquarter(float2 a) {
 // multiply by a compile-time unit-circle constant (c, -s) forward / (c, +s) inverse
 template <bool INV>
 __device__ __forceinline__ float2 cmulc(float2 a, float c, float s) {
+#if B2F_PACKED
+  const float2 t = up2(mul2(pk2(s, s), pk2(a.y, a.x)));  // (s a.y, s a.x)
+  return up2(fma2(pk2(c, c), pk2(a.x, a.y), INV ? pk2(-t.x, t.y) : pk2(t.x, -t.y)));
+#else
   return INV ? make_float2(a.x * c - a.y * s, a.x * s + a.y * c) : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+#endif
 }
 
 #define B2F_SQRT1_2 0.70710678118654752440f
@@ -239,14 +300,21 @@ __device__ __forceinline__ float2 rfft_dc(float2 c0) {
 
 // the same pair with 0.5, the scaling and the quarter turn folded into the table entry hw = 0.5*scale*i*w
 // (forward) or its conjugate (inverse) and hs = 0.5*scale: out_i = hs*S + hw*D, out_j = conj(hs*S - hw*D) with
-// S = A + conj(B), D = conj(B) - A. 12 instructions per pair.
+// S = A + conj(B), D = conj(B) - A. 6 packed instructions per pair (12 scalar).
 template <bool INV>
 __device__ __forceinline__ void rfft_pair_folded(float2 &A, float2 &B, float2 hw, float hs) {
+#if B2F_PACKED
+  const float2 Bc = make_float2(B.x, -B.y);
+  const float2 S = cadd(A, Bc), D = csub(Bc, A), P = cmul(D, hw);
+  A = up2(fma2(pk2(hs, hs), pk2(S.x, S.y), pk2(P.x, P.y)));
+  B = up2(fma2(pk2(hs, -hs), pk2(S.x, S.y), pk2(-P.x, P.y)));
+#else
   const float sx = A.x + B.x, sy = A.y - B.y;
   const float dx = B.x - A.x, dy = -B.y - A.y;
   const float px = hw.x * dx - hw.y * dy, py = hw.x * dy + hw.y * dx;
   A = make_float2(fmaf(hs, sx, px), fmaf(hs, sy, py));
   B = make_float2(fmaf(hs, sx, -px), fmaf(-hs, sy, py));
+#endif
 }
 
 }  // namespace b2f

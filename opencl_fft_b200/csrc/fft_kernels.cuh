@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   float2 *sm = smem + lt * FftGeom<LOGN>::SMEM;
   auto load = [&](int idx, int) { return active ? src[idx] : make_float2(0.f, 0.f); };
   auto store = [&](int idx, float2 v, int) {
-    if (active) dst[idx] = make_float2(v.x * scale, v.y * scale);
+    if (active) dst[idx] = cscale(v, scale);
   };
   fft_run<LOGN, INV>(load, store, sm, tw, t, CtaSync());
 }
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   float2 *dst = out + (active ? b : 0) * N;
   float2 *sm = smem + lt * FftGeom<LOGN>::SMEM;
   auto load = [&](int idx, int) { return active ? src[idx] : make_float2(0.f, 0.f); };
-  auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = make_float2(v.x * scale, v.y * scale); };
+  auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = cscale(v, scale); };
   fft_run<LOGN, false, true>(load, store, sm, tw, t, CtaSync());
   __syncthreads();
   if (!active) return;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   for (int m = 0; m < 8; m++) {
     if (m == 0 && t == 0) {
       dst[0] = make_float2((x[0].x + x[0].y) * hs, (x[0].x - x[0].y) * hs);   // packed (DC, Nyquist)
-      dst[N / 2] = make_float2(x[8].x * scale, x[8].y * scale);               // never visited by the reference (Q3)
+      dst[N / 2] = cscale(x[8], scale);               // never visited by the reference (Q3)
       continue;
     }
     const int pm = (t == 0) ? 16 - m : 15 - m;

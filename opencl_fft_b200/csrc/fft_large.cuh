@@ -18,6 +18,7 @@
 #pragma once
 
 #include "fft_core.cuh"
+#include "tma_utils.cuh"
 
 // Build-time knobs kept for re-measurement. Measured on B200 (2048 x 32768 complex): twiddles in registers or
 // streamed from L2 at 2 CTAs/SM: 0.365 ms either way; 3 or 4 CTAs/SM (streamed twiddles, no spills): 0.43 ms --
@@ -47,6 +48,30 @@ struct LargeGeom {
   static constexpr int SMEM_B = RB * (G2::SMEM + 1) * (int)sizeof(float2);
 };
 
+// The inter-step twiddles of one thread: W_N^(n2*k1) for its column n2 and the E rows k1 its last pass stores.
+template <int LOG1, int LOG2, bool INV>
+__device__ __forceinline__ void large_cols_twiddles(float2 (&wreg)[FftGeom<LOG1>::E], const float2 *__restrict__ twl,
+                                                    int n2, int t) {
+  constexpr int N2 = 1 << LOG2;
+#pragma unroll
+  for (int s = 0; s < FftGeom<LOG1>::E; s++) {
+    const int k1 = last_pass_index<LOG1>(t, s);
+    float2 w = __ldg(&twl[(size_t)k1 * N2 + n2]);
+    if (INV) w.y = -w.y;
+    wreg[s] = w;
+  }
+}
+// One column of one transform: src/dst already point at element n2 of the transform / scratch matrix.
+template <int LOG1, int LOG2, bool INV>
+__device__ __forceinline__ void large_cols_body(const float2 *src, float2 *dst, float2 *sm,
+                                                const float2 *__restrict__ tw1,
+                                                const float2 (&wreg)[FftGeom<LOG1>::E], int t) {
+  constexpr int N2 = 1 << LOG2;
+  auto load = [&](int idx, int) { return src[(size_t)idx * N2]; };
+  auto store = [&](int idx, float2 v, int slot) { dst[(size_t)idx * N2] = cmul(v, wreg[slot]); };
+  fft_run<LOG1, INV>(load, store, sm, tw1, t, CtaSync());
+}
+
 // grid = (N2 / C, batch slots). twl: [N1][N2] table, twl[k1*N2 + n2] = W_N^(n2*k1) (forward sign).
 template <int LOG1, int LOG2, bool INV>
 __global__ void __launch_bounds__(256, LARGE_COLS_MINB)
@@ -61,28 +86,22 @@ __global__ void __launch_bounds__(256, LARGE_COLS_MINB)
 #if LARGE_COLS_TW_REGS
   // this thread's inter-step twiddles, fixed for every transform of the batch
   float2 wreg[E];
-#pragma unroll
-  for (int s = 0; s < E; s++) {
-    const int k1 = last_pass_index<LOG1>(t, s);
-    float2 w = __ldg(&twl[(size_t)k1 * N2 + n2]);
-    if (INV) w.y = -w.y;
-    wreg[s] = w;
-  }
+  large_cols_twiddles<LOG1, LOG2, INV>(wreg, twl, n2, t);
 #endif
   for (int b = blockIdx.y; b < batch; b += gridDim.y) {
     const float2 *src = in + (size_t)b * N + n2;
     float2 *dst = scratch + (size_t)b * N + n2;
-    auto load = [&](int idx, int) { return src[(size_t)idx * N2]; };
 #if LARGE_COLS_TW_REGS
-    auto store = [&](int idx, float2 v, int slot) { dst[(size_t)idx * N2] = cmul(v, wreg[slot]); };
+    large_cols_body<LOG1, LOG2, INV>(src, dst, sm, tw1, wreg, t);
 #else
+    auto load = [&](int idx, int) { return src[(size_t)idx * N2]; };
     auto store = [&](int idx, float2 v, int) {
       float2 w = __ldg(&twl[(size_t)idx * N2 + n2]);
       if (INV) w.y = -w.y;
       dst[(size_t)idx * N2] = cmul(v, w);
     };
-#endif
     fft_run<LOG1, INV>(load, store, sm, tw1, t, CtaSync());
+#endif
     __syncthreads();  // shared memory is reused by the next transform
   }
 }
@@ -92,16 +111,21 @@ __global__ void __launch_bounds__(256, LARGE_COLS_MINB)
 // owns 8 rows {8g..8g+7} and their mirrors {N1-k} (row 0 mirrors itself; its slot hosts row N1/2), so both
 // members of every pair (i, N-i) = ((k1,k2), (N1-k1, N2-1-k2)) sit in its shared memory; every pair is
 // evaluated once (folded table hw, scale included) and both members are stored, in 64-byte runs.
-template <int LOG1, int LOG2, bool INV, bool REAL>
-__global__ void __launch_bounds__(256)
-    large_rows_kernel(const float2 *scratch, float2 *out, const float2 *__restrict__ tw2,
-                      const float2 *__restrict__ hw, int batch, float scale) {
+// One row group g of one transform: scratch_b / out_b point at the transform's scratch matrix / output.
+// CG: read the scratch with ld.global.cg (it was written by other CTAs of the cluster in this very launch).
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// after_reads(): called by every thread once the whole CTA holds its rows in shared memory, i.e. when the
+// scratch has been consumed and before anything is written to `out`.
+template <int LOG1, int LOG2, bool INV, bool REAL, bool CG, class Hook = NoHook, bool TWS = false>
+__device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 *out_b, float2 *smem,
+                                                const float2 *__restrict__ tw2, const float2 *__restrict__ hw,
+                                                float scale, int g, Hook after_reads = Hook()) {
   using L = LargeGeom<LOG1, LOG2>;
   constexpr int N1 = L::N1, N2 = L::N2, N = L::N, RB = L::RB, T2 = L::G2::T;
   static_assert(!REAL || RB == 16, "mirrored row groups are 8 + 8");
-  extern __shared__ float2 smem[];
   const int t = threadIdx.x % T2, row = threadIdx.x / T2;
-  const int g = blockIdx.x;
   auto row_of = [&](int rr) -> int {
     if (!REAL) return g * RB + rr;
     if (rr < 8) return g * 8 + rr;
@@ -111,69 +135,253 @@ __global__ void __launch_bounds__(256)
   constexpr int RS = REAL ? L::ROWSTRIDE_R : L::ROWSTRIDE_C;
   float2 *sm = smem + row * RS;
   const int k1_fft = row_of(row);
-  for (int b = blockIdx.y; b < batch; b += gridDim.y) {
-    const float2 *src = scratch + (size_t)b * N + (size_t)k1_fft * N2;
-    auto load = [&](int idx, int) { return src[idx]; };
-    auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = v; };
-    fft_run<LOG2, INV, true>(load, store, sm, tw2, t, CtaSync());
-    __syncthreads();
-    float2 *dst = out + (size_t)b * N;
-    if (!REAL) {
-      // transposed write-out: consecutive threads take consecutive rows (k1), i.e. consecutive addresses
-      const int rr = threadIdx.x % RB;
-      const float2 *smr = smem + rr * RS;
-      for (int k2 = threadIdx.x / RB; k2 < N2; k2 += L::THREADS / RB) {
-        float2 v = smr[pad_idx(k2)];
-        dst[(size_t)k2 * N1 + g * RB + rr] = make_float2(v.x * scale, v.y * scale);
+  const float2 *src = scratch_b + (size_t)k1_fft * N2;
+  auto load = [&](int idx, int) { return CG ? __ldcg(&src[idx]) : src[idx]; };
+  auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = v; };
+  // REAL: the folded split twiddles of this thread's N2/32 pairs, requested before the transform so that their
+  // latency (L2: every CTA walks a different 16 KB slice of the table) is off the write-out's critical path
+  constexpr int NPAIR = REAL ? N2 / (L::THREADS / 8) : 1;
+  float2 hwr[NPAIR];
+  if constexpr (REAL) {
+    const int k1 = g * 8 + threadIdx.x % 8;
+#pragma unroll
+    for (int m = 0; m < NPAIR; m++) {
+      const int i = k1 + N1 * (threadIdx.x / 8 + m * (L::THREADS / 8));
+      hwr[m] = __ldg(&hw[i < N - i ? i : N - i]);
+    }
+  }
+  fft_run<LOG2, INV, true, false, TWS>(load, store, sm, tw2, t, CtaSync());
+  __syncthreads();
+  after_reads();
+  float2 *dst = out_b;
+  if (!REAL) {
+    // transposed write-out: consecutive threads take consecutive rows (k1), i.e. consecutive addresses
+    const int rr = threadIdx.x % RB;
+    const float2 *smr = smem + rr * RS;
+    for (int k2 = threadIdx.x / RB; k2 < N2; k2 += L::THREADS / RB) {
+      float2 v = smr[pad_idx(k2)];
+      dst[(size_t)k2 * N1 + g * RB + rr] = cscale(v, scale);
+    }
+  } else {
+    // one pair per (direct row rr < 8, k2): low member i = k1 + N1*k2 when i < N/2, else its partner is
+    const int rr = threadIdx.x % 8;
+    const int k1 = g * 8 + rr;              // direct row, in [0, N1/2)
+    const bool zero = (k1 == 0);
+    const int prr = zero ? 0 : rr + 8;      // row 0 pairs with itself
+    const int k1p = zero ? 0 : N1 - k1;
+    const float2 *smr = smem + rr * RS, *smp = smem + prr * RS;
+    const float hs = 0.5f * scale;
+    // rows 1..N1/2-1: all N2 values of k2, the pair's other member is on the mirror row.
+    // row 0: pairs (0,k2) <-> (0,N2-k2) for k2 in [1, N2/2), plus the two self-paired elements.
+#pragma unroll
+    for (int m = 0; m < NPAIR; m++) {
+      const int k2 = threadIdx.x / 8 + m * (L::THREADS / 8);
+      const int pk2 = zero ? N2 - k2 : N2 - 1 - k2;
+      if (zero && (k2 == 0 || k2 >= N2 / 2)) {
+        if (k2 == 0) {
+          const float2 v = smr[pad_idx(0)];
+          dst[0] = make_float2((v.x + v.y) * hs, (v.x - v.y) * hs);
+        } else if (k2 == N2 / 2) {
+          const float2 v = smr[pad_idx(k2)];
+          dst[N / 2] = cscale(v, scale);  // never visited by the reference (Q3)
+        }
+        continue;
       }
-    } else {
-      // one pair per (direct row rr < 8, k2): low member i = k1 + N1*k2 when i < N/2, else its partner is
-      const int rr = threadIdx.x % 8;
-      const int k1 = g * 8 + rr;              // direct row, in [0, N1/2)
-      const bool zero = (k1 == 0);
-      const int prr = zero ? 0 : rr + 8;      // row 0 pairs with itself
-      const int k1p = zero ? 0 : N1 - k1;
-      const float2 *smr = smem + rr * RS, *smp = smem + prr * RS;
-      const float hs = 0.5f * scale;
-      // rows 1..N1/2-1: all N2 values of k2, the pair's other member is on the mirror row.
-      // row 0: pairs (0,k2) <-> (0,N2-k2) for k2 in [1, N2/2), plus the two self-paired elements.
-      for (int k2 = threadIdx.x / 8; k2 < N2; k2 += L::THREADS / 8) {
-        const int pk2 = zero ? N2 - k2 : N2 - 1 - k2;
-        if (zero && (k2 == 0 || k2 >= N2 / 2)) {
-          if (k2 == 0) {
-            const float2 v = smr[pad_idx(0)];
-            dst[0] = make_float2((v.x + v.y) * hs, (v.x - v.y) * hs);
-          } else if (k2 == N2 / 2) {
-            const float2 v = smr[pad_idx(k2)];
-            dst[N / 2] = make_float2(v.x * scale, v.y * scale);  // never visited by the reference (Q3)
-          }
-          continue;
-        }
-        float2 a = smr[pad_idx(k2)], bb = smp[pad_idx(pk2)];
-        const int i = k1 + N1 * k2, j = k1p + N1 * pk2;  // i + j == N
-        if (i < j) {
-          rfft_pair_folded<false>(a, bb, __ldg(&hw[i]), hs);
-        } else {
-          rfft_pair_folded<false>(bb, a, __ldg(&hw[j]), hs);
-        }
+      float2 a = smr[pad_idx(k2)], bb = smp[pad_idx(pk2)];
+      const int i = k1 + N1 * k2, j = k1p + N1 * pk2;  // i + j == N
+      if (i < j) {
+        rfft_pair_folded<false>(a, bb, hwr[m], hs);
+      } else {
+        rfft_pair_folded<false>(bb, a, hwr[m], hs);
+      }
+      dst[i] = a;
+      dst[j] = bb;
+    }
+    // the self-mirrored row N1/2 lives in slot 8 of group 0: pairs (N1/2,k2) <-> (N1/2, N2-1-k2)
+    if (g == 0) {
+      const float2 *smh = smem + 8 * RS;
+      for (int k2 = threadIdx.x; k2 < N2 / 2; k2 += L::THREADS) {
+        const int pk2 = N2 - 1 - k2;
+        float2 a = smh[pad_idx(k2)], bb = smh[pad_idx(pk2)];
+        const int i = N1 / 2 + N1 * k2, j = N1 / 2 + N1 * pk2;
+        rfft_pair_folded<false>(a, bb, __ldg(&hw[i]), hs);
         dst[i] = a;
         dst[j] = bb;
       }
-      // the self-mirrored row N1/2 lives in slot 8 of group 0: pairs (N1/2,k2) <-> (N1/2, N2-1-k2)
-      if (g == 0) {
-        const float2 *smh = smem + 8 * RS;
-        for (int k2 = threadIdx.x; k2 < N2 / 2; k2 += L::THREADS) {
-          const int pk2 = N2 - 1 - k2;
-          float2 a = smh[pad_idx(k2)], bb = smh[pad_idx(pk2)];
-          const int i = N1 / 2 + N1 * k2, j = N1 / 2 + N1 * pk2;
-          rfft_pair_folded<false>(a, bb, __ldg(&hw[i]), hs);
-          dst[i] = a;
-          dst[j] = bb;
-        }
-      }
     }
+  }
+}
+
+template <int LOG1, int LOG2, bool INV, bool REAL>
+__global__ void __launch_bounds__(256)
+    large_rows_kernel(const float2 *scratch, float2 *out, const float2 *__restrict__ tw2,
+                      const float2 *__restrict__ hw, int batch, float scale) {
+  constexpr int N = 1 << (LOG1 + LOG2);
+  extern __shared__ float2 smem[];
+  // last transform first: the tail of what the columns kernel has just written is still in the 126 MB L2
+  for (int b = batch - 1 - (int)blockIdx.y; b >= 0; b -= gridDim.y) {
+    large_rows_body<LOG1, LOG2, INV, REAL, false>(scratch + (size_t)b * N, out + (size_t)b * N, smem, tw2, hw, scale,
+                                                  blockIdx.x);
     __syncthreads();
   }
+}
+
+// ---- both steps in ONE launch: an 8-CTA thread-block cluster per transform, scratch private to the cluster ---------
+// CTA r of a cluster is column group r in the first step and row group r in the second (N2/C == N1/RB == 8 for
+// N = 2^15). The scratch matrix belongs to the cluster -- three buffers of N complex values, reused for every
+// transform the cluster works through -- so the ~28 MB of scratch of a whole grid stays resident in the 126 MB
+// L2 and HBM sees the algorithmic bytes only (the two-launch path moves every transform through HBM twice).
+//
+// Software pipeline of one CTA (k = iteration, b_k = the cluster's k-th transform):
+//   cp.async prefetch of the columns of b_{k+2} into a shared-memory stage   (HBM latency off the critical path)
+//   columns of b_{k+1}: stage -> N1-point FFTs -> twiddle -> scratch[(k+1) % 3]
+//   wait(k)      "every column group of b_k is in the scratch"; signalled before the step above, so the skew
+//                between the 8 CTAs and the store drain hide behind it
+//   rows of b_k: scratch[k % 3] (ld.global.cg, L2) -> N2-point FFTs -> signal(k+1) -> [split] -> out
+// Three buffers: the columns of b_{k+1} are written while a slower CTA of the cluster may still read the rows of
+// b_{k-1}; it cannot be further behind, because this CTA passed wait(k-1), i.e. everybody finished rows b_{k-2}.
+template <int LOG1, int LOG2>
+struct FusedGeom {
+  using L = LargeGeom<LOG1, LOG2>;
+  static constexpr int WORK_F2 = (L::SMEM_A > L::SMEM_B ? L::SMEM_A : L::SMEM_B) / (int)sizeof(float2);
+  static constexpr int WORK_F2_AL = (WORK_F2 + 1) & ~1;            // 16-byte aligned stage behind it
+  static constexpr int STAGE_F2 = L::N1 * L::C;                     // [N1][C] float2
+  static constexpr int TW1_F2 = sched_tw_total(L::G1::S) + 1, TW2_F2 = sched_tw_total(L::G2::S) + 1;  // pass twiddles
+  static constexpr int SMEM_BYTES = (WORK_F2_AL + STAGE_F2 + TW1_F2 + TW2_F2) * (int)sizeof(float2);
+  static constexpr int NBUF = 3;
+};
+
+// MINB: resident CTAs per SM the register budget is set for. 2: all E inter-step twiddles of a thread stay in
+// registers for the whole launch (128 registers). 3: only 4 + 3 of them do -- the thread's rows are k1 = t + 32a + 8b,
+// so W^(n2 k1) = W^(n2 (t + 32a)) * W^(n2 8b), both factors exact table entries, one extra rounding -- which fits
+// 85 registers: 24 warps per SM instead of 16 hide more of the instruction and barrier latency of the two steps.
+template <int LOG1, int LOG2, bool INV, bool REAL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    large_fused_kernel(const float2 *in, float2 *out, float2 *scratch, const float2 *__restrict__ tw1,
+                       const float2 *__restrict__ tw2, const float2 *__restrict__ twl,
+                       const float2 *__restrict__ hw, int batch, float scale, int dbg) {
+  using L = LargeGeom<LOG1, LOG2>;
+  using F = FusedGeom<LOG1, LOG2>;
+  constexpr int N1 = L::N1, N2 = L::N2, N = L::N, C = L::C, E = L::G1::E, S = 8;
+  static_assert(L::N2 / L::C == S && L::N1 / L::RB == S, "one column group and one row group per CTA of the cluster");
+  static_assert(C % 2 == 0 && (N1 * C / 2) % 256 == 0, "16-byte cp.async chunks, whole rounds of 256 threads");
+  extern __shared__ __align__(16) float2 smem[];
+  float2 *stage = smem + F::WORK_F2_AL;
+  // the two plans' pass twiddles (3 KB) live in shared memory: with 2-3 CTAs of this size per SM the L1 that is
+  // left is too small to keep them resident next to the streaming traffic
+  float2 *stw1 = stage + F::STAGE_F2, *stw2 = stw1 + F::TW1_F2;
+  for (int i = threadIdx.x; i < F::TW1_F2 - 1; i += 256) stw1[i] = __ldg(&tw1[i]);
+  for (int i = threadIdx.x; i < F::TW2_F2 - 1; i += 256) stw2[i] = __ldg(&tw2[i]);
+  const int rank = blockIdx.x % S, cid = blockIdx.x / S, ncl = gridDim.x / S;
+  const int c = threadIdx.x % C, t = threadIdx.x / C;
+  const int n2 = rank * C + c;
+  float2 *smc = smem + c * L::G1::SMEM;
+  if (cid >= batch) return;  // whole cluster
+  constexpr bool FACTORED = MINB >= 3;
+  static_assert(!FACTORED || (LOG1 == 7 && E == 16), "factored twiddles assume rows k1 = t + 8 r, r = 4a + b");
+  float2 wreg[FACTORED ? 4 : E], gpow[4];
+  if constexpr (FACTORED) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      wreg[a] = __ldg(&twl[(size_t)(t + 32 * a) * N2 + n2]);
+      gpow[a] = __ldg(&twl[(size_t)(8 * a) * N2 + n2]);
+      if (INV) wreg[a].y = -wreg[a].y, gpow[a].y = -gpow[a].y;
+    }
+  } else {
+    large_cols_twiddles<LOG1, LOG2, INV>(wreg, twl, n2, t);
+  }
+  float2 *scr = scratch + (size_t)cid * F::NBUF * N;
+
+  // columns [rank*C, rank*C + C) of transform b -> stage[n1][c], 16 bytes (two columns) per cp.async
+  auto prefetch = [&](int b) {
+    const float2 *src = in + (size_t)b * N + rank * C;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
+#pragma unroll
+    for (int q = threadIdx.x; q < N1 * C / 2; q += 256) {
+      const int row = q / (C / 2), c2 = q % (C / 2);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)(row * C + 2 * c2) * 8u),
+                   "l"(src + (size_t)row * N2 + 2 * c2)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto cols = [&](int buf) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();  // everybody's part of the stage has landed
+    float2 *dst = scr + (size_t)buf * N + n2;
+    auto load = [&](int idx, int) { return stage[idx * C + c]; };
+    auto store = [&](int idx, float2 v, int slot) {
+      float2 w;
+      if constexpr (FACTORED)
+        w = (slot & 3) ? cmul(wreg[slot >> 2], gpow[slot & 3]) : wreg[slot >> 2];
+      else
+        w = wreg[slot];
+      if (!(dbg & 4)) dst[(size_t)idx * N2] = cmul(v, w);
+    };
+    fft_run<LOG1, INV, false, false, true>(load, store, smc, stw1, t, CtaSync());
+    __syncthreads();  // stage and work buffer are free again
+  };
+
+  // All-to-all barrier of the cluster on shared-memory mbarriers (two, alternating by iteration): after a CTA
+  // barrier, 8 lanes of warp 0 arrive (release.cluster) on the current mbarrier of the 8 CTAs; everybody waits on
+  // its own. Unlike barrier.cluster.arrive/wait -- MEMBAR.ALL.GPU in every warp, CCTL.IVALL (L1 invalidation,
+  // twiddle tables included) after every wait -- one warp fences and no cache is invalidated; the scratch is
+  // read with ld.global.cg, which does not look in L1.
+  __shared__ __align__(8) unsigned long long xbar[2];
+  const uint32_t xb0 = tma::smem_u32(&xbar[0]);
+  if (threadIdx.x == 0) {
+    tma::mbar_init(xb0, S);
+    tma::mbar_init(xb0 + 8, S);
+    tma::fence_barrier_init();
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  int bars = 0;  // barriers signalled so far; barrier j lives on xbar[j & 1], phase parity (j >> 1) & 1
+  auto signal = [&]() {  // caller has just passed a __syncthreads() after the work being published
+    if (threadIdx.x < S) {
+      const uint32_t remote = tma::map_to_rank(xb0 + 8 * (bars & 1), threadIdx.x);
+      if (dbg & 1)
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+      else
+        tma::mbar_arrive_cluster_release(remote);
+    }
+    bars++;
+  };
+  auto wait_for = [&](int j) {
+    if (!(dbg & 2)) tma::mbar_wait(xb0 + 8 * (j & 1), (j >> 1) & 1);
+  };
+
+  int b = cid, nb = cid + ncl, k = 0, j = 0;
+  prefetch(b);
+  cols(0);
+  if (nb < batch) prefetch(nb);
+  signal();
+  while (true) {
+    const bool more = nb < batch;
+    const int kn = (k + 1 == F::NBUF) ? 0 : k + 1;
+    if (more) {
+      cols(kn);
+      if (nb + ncl < batch) prefetch(nb + ncl);
+    }
+    wait_for(j);
+    // barrier j+1 = "my columns of b_{k+1} are in the scratch and I have consumed the rows of b_k": signalled
+    // from inside the rows step, before its stores to `out`, so that the release does not wait for those
+    auto hook = [&]() {
+      if (more) signal();
+    };
+    if (!(dbg & 8))
+      large_rows_body<LOG1, LOG2, INV, REAL, true, decltype(hook), true>(scr + (size_t)k * N, out + (size_t)b * N, smem,
+                                                                         stw2, hw, scale, rank, hook);
+    else
+      hook();
+    __syncthreads();
+    if (!more) break;
+    b = nb;
+    nb += ncl;
+    k = kn;
+    j++;
+  }
+  // nobody leaves while a sibling may still arrive on its mbarriers
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // element-wise real-FFT split (forward, after the complex transform) / unsplit (inverse, before it)

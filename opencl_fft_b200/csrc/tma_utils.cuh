@@ -32,6 +32,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier of another CTA of the cluster; release at cluster scope: this thread's earlier writes --
+// and, through a preceding bar.sync, its CTA's -- are visible to whoever observes the phase completing
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t remote_mbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_mbar) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(mbar)

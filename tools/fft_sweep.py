@@ -13,6 +13,8 @@ import opencl_fft_b200 as eng  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--mb", type=int, default=512, help="input megabytes per launch (>> L2)")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--logn-min", type=int, default=4)
+ap.add_argument("--logn-max", type=int, default=16)
 args = ap.parse_args()
 peak = 6544.7
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -37,7 +39,7 @@ rows = []
 total = args.mb << 20
 x = torch.randn(2, total // 4, device="cuda")
 y = torch.empty_like(x)
-for logn in range(4, 17):
+for logn in range(args.logn_min, args.logn_max + 1):
     N = 1 << logn
     batch = total // (8 * N)
     for kind in ("c2c", "r2c", "c2r"):
