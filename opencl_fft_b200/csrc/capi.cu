@@ -346,26 +346,37 @@ struct LargePlan {
       if (p) cudaFree(p);
     d_tw1 = d_tw2 = d_twl = d_scratch = d_fscratch = nullptr;
   }
-  template <int L1, int L2, bool INV, bool REAL = false>
-  int run_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw = nullptr) {
+  template <int L1, int L2, bool INV, bool REAL, int RBT>
+  int run_tt(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw) {
     using L = LargeGeom<L1, L2>;
+    using R = RowsGeom<L1, L2, RBT>;
     int rc;
     if ((rc = set_smem(large_cols_kernel<L1, L2, INV>, L::SMEM_A))) return rc;
-    if ((rc = set_smem(large_rows_kernel<L1, L2, INV, REAL>, L::SMEM_B))) return rc;
+    if ((rc = set_smem(large_rows_kernel<L1, L2, INV, REAL, RBT>, R::SMEM))) return rc;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
       const int nb = batch - b0 < chunk ? batch - b0 : chunk;
-      const int gxa = L::N2 / L::C, gxb = L::N1 / L::RB;
-      int gya = (592 + gxa - 1) / gxa, gyb = (592 + gxb - 1) / gxb;
+      const int gxa = L::N2 / L::C, gxb = R::GROUPS;
+      // ~4 x 148 CTAs of 256 threads (2 x 148 of 512) per launch, each looping over its share of the batch
+      int gya = (592 + gxa - 1) / gxa, gyb = (592 * 256 / R::THREADS + gxb - 1) / gxb;
       if (gya > nb) gya = nb;
       if (gyb > nb) gyb = nb;
       const float2 *src = in + (size_t)b0 * L::N;
       float2 *dst = out + (size_t)b0 * L::N;
       large_cols_kernel<L1, L2, INV><<<dim3(gxa, gya), L::THREADS, L::SMEM_A, st>>>(src, d_scratch, d_tw1, d_twl, nb);
       CK(cudaGetLastError());
-      large_rows_kernel<L1, L2, INV, REAL><<<dim3(gxb, gyb), L::THREADS, L::SMEM_B, st>>>(d_scratch, dst, d_tw2, hw, nb, scale);
+      large_rows_kernel<L1, L2, INV, REAL, RBT><<<dim3(gxb, gyb), R::THREADS, R::SMEM, st>>>(d_scratch, dst, d_tw2, hw, nb, scale);
       CK(cudaGetLastError());
     }
     return B2F_OK;
+  }
+  template <int L1, int L2, bool INV, bool REAL = false>
+  int run_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw = nullptr) {
+    constexpr int RB = LargeGeom<L1, L2>::RB;
+    if constexpr (REAL) {
+      static const bool rb16 = getenv("B2F_ROWS_RB16") != nullptr;
+      if (!rb16) return run_tt<L1, L2, INV, true, 2 * RB>(in, out, batch, scale, st, hw);
+    }
+    return run_tt<L1, L2, INV, REAL, RB>(in, out, batch, scale, st, hw);
   }
   // Both steps in one launch on 8-CTA clusters with cluster-private, L2-resident scratch (fft_large.cuh,
   // large_fused_kernel): N = 2^15 only (8 column groups == 8 row groups == the portable cluster size).

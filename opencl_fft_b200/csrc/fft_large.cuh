@@ -118,35 +118,41 @@ struct NoHook {
 };
 // after_reads(): called by every thread once the whole CTA holds its rows in shared memory, i.e. when the
 // scratch has been consumed and before anything is written to `out`.
-template <int LOG1, int LOG2, bool INV, bool REAL, bool CG, class Hook = NoHook, bool TWS = false>
+// RBT: rows per CTA (RBT * T2 threads). REAL with RBT = 32 (16 direct rows + 16 mirrors) makes the direct members'
+// runs whole 128-byte lines (the mirrors' runs are 120 + 8 bytes); RBT = 16 gives 64-byte runs.
+template <int LOG1, int LOG2, bool INV, bool REAL, bool CG, class Hook = NoHook, bool TWS = false,
+          int RBT = LargeGeom<LOG1, LOG2>::RB>
 __device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 *out_b, float2 *smem,
                                                 const float2 *__restrict__ tw2, const float2 *__restrict__ hw,
                                                 float scale, int g, Hook after_reads = Hook()) {
   using L = LargeGeom<LOG1, LOG2>;
-  constexpr int N1 = L::N1, N2 = L::N2, N = L::N, RB = L::RB, T2 = L::G2::T;
-  static_assert(!REAL || RB == 16, "mirrored row groups are 8 + 8");
+  constexpr int N1 = L::N1, N2 = L::N2, N = L::N, RB = RBT, T2 = L::G2::T, NTHR = RBT * T2, RH = RBT / 2;
+  static_assert(!REAL || RB == 16 || RB == 32, "mirrored row groups are 8 + 8 or 16 + 16");
   const int t = threadIdx.x % T2, row = threadIdx.x / T2;
   auto row_of = [&](int rr) -> int {
     if (!REAL) return g * RB + rr;
-    if (rr < 8) return g * 8 + rr;
-    const int d = g * 8 + (rr - 8);
+    if (rr < RH) return g * RH + rr;
+    const int d = g * RH + (rr - RH);
     return d == 0 ? N1 / 2 : N1 - d;
   };
-  constexpr int RS = REAL ? L::ROWSTRIDE_R : L::ROWSTRIDE_C;
+  // per-row stride in float2: odd when a half-warp reads one element from each of 16 rows, == 2 (mod 16) when it
+  // reads two adjacent elements from each of 8 rows
+  constexpr int RS = (REAL && RH == 8) ? L::ROWSTRIDE_R : L::ROWSTRIDE_C;
   float2 *sm = smem + row * RS;
   const int k1_fft = row_of(row);
   const float2 *src = scratch_b + (size_t)k1_fft * N2;
   auto load = [&](int idx, int) { return CG ? __ldcg(&src[idx]) : src[idx]; };
   auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = v; };
-  // REAL: the folded split twiddles of this thread's N2/32 pairs, requested before the transform so that their
-  // latency (L2: every CTA walks a different 16 KB slice of the table) is off the write-out's critical path
-  constexpr int NPAIR = REAL ? N2 / (L::THREADS / 8) : 1;
+  // REAL: the folded split twiddles of this thread's pairs, requested before the transform so that their
+  // latency (L2: every CTA walks a different slice of the table) is off the write-out's critical path
+  constexpr int KSTEP = NTHR / RH;  // k2 values covered per round of the pair loop
+  constexpr int NPAIR = REAL ? N2 / KSTEP : 1;
   float2 hwr[NPAIR];
   if constexpr (REAL) {
-    const int k1 = g * 8 + threadIdx.x % 8;
+    const int k1 = g * RH + threadIdx.x % RH;
 #pragma unroll
     for (int m = 0; m < NPAIR; m++) {
-      const int i = k1 + N1 * (threadIdx.x / 8 + m * (L::THREADS / 8));
+      const int i = k1 + N1 * (threadIdx.x / RH + m * KSTEP);
       hwr[m] = __ldg(&hw[i < N - i ? i : N - i]);
     }
   }
@@ -158,16 +164,16 @@ __device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 
     // transposed write-out: consecutive threads take consecutive rows (k1), i.e. consecutive addresses
     const int rr = threadIdx.x % RB;
     const float2 *smr = smem + rr * RS;
-    for (int k2 = threadIdx.x / RB; k2 < N2; k2 += L::THREADS / RB) {
+    for (int k2 = threadIdx.x / RB; k2 < N2; k2 += NTHR / RB) {
       float2 v = smr[pad_idx(k2)];
       dst[(size_t)k2 * N1 + g * RB + rr] = cscale(v, scale);
     }
   } else {
-    // one pair per (direct row rr < 8, k2): low member i = k1 + N1*k2 when i < N/2, else its partner is
-    const int rr = threadIdx.x % 8;
-    const int k1 = g * 8 + rr;              // direct row, in [0, N1/2)
+    // one pair per (direct row rr < RH, k2): low member i = k1 + N1*k2 when i < N/2, else its partner is
+    const int rr = threadIdx.x % RH;
+    const int k1 = g * RH + rr;             // direct row, in [0, N1/2)
     const bool zero = (k1 == 0);
-    const int prr = zero ? 0 : rr + 8;      // row 0 pairs with itself
+    const int prr = zero ? 0 : rr + RH;     // row 0 pairs with itself
     const int k1p = zero ? 0 : N1 - k1;
     const float2 *smr = smem + rr * RS, *smp = smem + prr * RS;
     const float hs = 0.5f * scale;
@@ -175,7 +181,7 @@ __device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 
     // row 0: pairs (0,k2) <-> (0,N2-k2) for k2 in [1, N2/2), plus the two self-paired elements.
 #pragma unroll
     for (int m = 0; m < NPAIR; m++) {
-      const int k2 = threadIdx.x / 8 + m * (L::THREADS / 8);
+      const int k2 = threadIdx.x / RH + m * KSTEP;
       const int pk2 = zero ? N2 - k2 : N2 - 1 - k2;
       if (zero && (k2 == 0 || k2 >= N2 / 2)) {
         if (k2 == 0) {
@@ -197,10 +203,10 @@ __device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 
       dst[i] = a;
       dst[j] = bb;
     }
-    // the self-mirrored row N1/2 lives in slot 8 of group 0: pairs (N1/2,k2) <-> (N1/2, N2-1-k2)
+    // the self-mirrored row N1/2 lives in slot RH of group 0: pairs (N1/2,k2) <-> (N1/2, N2-1-k2)
     if (g == 0) {
-      const float2 *smh = smem + 8 * RS;
-      for (int k2 = threadIdx.x; k2 < N2 / 2; k2 += L::THREADS) {
+      const float2 *smh = smem + RH * RS;
+      for (int k2 = threadIdx.x; k2 < N2 / 2; k2 += NTHR) {
         const int pk2 = N2 - 1 - k2;
         float2 a = smh[pad_idx(k2)], bb = smh[pad_idx(pk2)];
         const int i = N1 / 2 + N1 * k2, j = N1 / 2 + N1 * pk2;
@@ -212,16 +218,26 @@ __device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 
   }
 }
 
-template <int LOG1, int LOG2, bool INV, bool REAL>
-__global__ void __launch_bounds__(256)
+// RBT rows per CTA: 16 (256 threads) for complex transforms; 32 (512 threads: 16 direct + 16 mirrored rows) for the
+// fused real split, 16 kept for comparison (B2F_ROWS_RB16=1). grid.x = N1 / RBT.
+template <int LOG1, int LOG2, int RBT>
+struct RowsGeom {
+  using L = LargeGeom<LOG1, LOG2>;
+  static constexpr int THREADS = RBT * L::G2::T;
+  static constexpr int GROUPS = L::N1 / RBT;
+  static constexpr int SMEM = RBT * (L::G2::SMEM + 1) * (int)sizeof(float2);
+};
+
+template <int LOG1, int LOG2, bool INV, bool REAL, int RBT>
+__global__ void __launch_bounds__(RowsGeom<LOG1, LOG2, RBT>::THREADS)
     large_rows_kernel(const float2 *scratch, float2 *out, const float2 *__restrict__ tw2,
                       const float2 *__restrict__ hw, int batch, float scale) {
   constexpr int N = 1 << (LOG1 + LOG2);
   extern __shared__ float2 smem[];
   // last transform first: the tail of what the columns kernel has just written is still in the 126 MB L2
   for (int b = batch - 1 - (int)blockIdx.y; b >= 0; b -= gridDim.y) {
-    large_rows_body<LOG1, LOG2, INV, REAL, false>(scratch + (size_t)b * N, out + (size_t)b * N, smem, tw2, hw, scale,
-                                                  blockIdx.x);
+    large_rows_body<LOG1, LOG2, INV, REAL, false, NoHook, false, RBT>(scratch + (size_t)b * N, out + (size_t)b * N, smem,
+                                                                      tw2, hw, scale, blockIdx.x);
     __syncthreads();
   }
 }
