@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
 // Register-level real transforms for N >= 128 (schedules whose first and last passes leave every thread
 // with the 16 values X[t + m*T], m = 0..15, T = N/16). The pair partner of element (t, m) is element
 // (T - t, 15 - m) [(0, 16 - m) for t = 0], so the split / unsplit needs ONE partner thread: the two swap
-// half of their values through a small shared-memory staging area, each evaluates its 8 pairs once.
+// half of their values through a small shared-memory staging area, each evaluates its 8 pairs once (the inverse
+// reads the partner's inputs from global memory instead and only hands the results over).
 // Against the generic kernels above this drops a full shared-memory round trip and halves the split
 // arithmetic: 0.5, the 1/N scaling and the quarter turn are folded into the table
 //   hw[i] = 0.5 * scale * i * w2[i]  (forward)      hw[i] = conj(0.5 * i * w2[i])  (inverse)
@@ -196,30 +197,26 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   const float2 *src = in + (active ? b : 0) * N;
   float2 *dst = out + (active ? b : 0) * N;
   float2 *sm = smem + lt * FftGeom<LOGN>::SMEM;
-  float2 x[16];
-#pragma unroll
-  for (int m = 0; m < 16; m++) x[m] = active ? __ldcs(src + t + m * T) : make_float2(0.f, 0.f);
+  // a thread reads its 8 low members X[t + m*T] and, straight from global memory, their partners X[N - (t + m*T)]
+  // (the values its partner thread will own): 16 loads as before, and no exchange before the unsplit
+  float2 x[16], hi[8];  // hi: unsplit high members, owned by the partner thread
   const int pt = (t == 0) ? 0 : T - t;
-  // exchange 1: my upper half to the partner
-#pragma unroll
-  for (int m = 8; m < 16; m++) sm[(m - 8) * T + t] = x[m];
-  __syncthreads();
-  float2 hi[8];  // unsplit high members, owned by the partner thread
+  const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int m = 0; m < 8; m++) {
-    const int pm = (t == 0) ? 16 - m : 15 - m;
+    const int i = t + m * T;
+    x[m] = active ? __ldcs(src + i) : zero2;
+    hi[m] = active ? __ldcs(src + (i == 0 ? N / 2 : N - i)) : zero2;  // element N/2 rides with (t, m) = (0, 0)
+  }
+#pragma unroll
+  for (int m = 0; m < 8; m++) {
     if (m == 0 && t == 0) {
-      x[0] = make_float2(x[0].x + x[0].y, x[0].x - x[0].y);
-      hi[0] = x[8];  // element N/2 passes through (it is this thread's own slot 8)
+      x[0] = make_float2(x[0].x + x[0].y, x[0].x - x[0].y);  // packed (DC, Nyquist); hi[0] = element N/2 passes through
       continue;
     }
-    float2 a = x[m], bb = sm[(pm - 8) * T + pt];
-    rfft_pair_folded<true>(a, bb, __ldg(&hw[t + m * T]), 0.5f);
-    x[m] = a;
-    hi[m] = bb;
+    rfft_pair_folded<true>(x[m], hi[m], __ldg(&hw[t + m * T]), 0.5f);
   }
-  __syncthreads();
-  // exchange 2: hand the high members back to their owners
+  // the one exchange: hand the high members to their owners
 #pragma unroll
   for (int m = 0; m < 8; m++) {
     const int pm = (t == 0) ? ((16 - m) & 15) : 15 - m;  // (t = 0, m = 0) parks element N/2 in slot 8
