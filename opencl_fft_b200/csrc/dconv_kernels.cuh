@@ -21,6 +21,11 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+// Two-lane FP32 (FFMA2 on register pairs, tap broadcast, a second window copy shifted by one sample for the odd
+// taps) was built and measured here: 50.6 TFLOP/s against 53.4 for scalar FFMA at config 4. FFMA2 halves the
+// instruction count of the inner loop but occupies the issue port like two FFMAs on B200 (tools/pk_probe.cu), so
+// nothing is freed for the shared-memory loads. The scalar form is the one kept.
+
 namespace b2f {
 
 namespace cg = cooperative_groups;
@@ -57,8 +62,9 @@ struct DconvArgs {
 template <int TN>
 __global__ void __launch_bounds__(kDcThreads) dconv_fir_kernel(DconvArgs a) {
   using G = DconvGeom<TN>;
-  __shared__ __align__(16) float xs[G::XS_PADDED];
-  __shared__ __align__(16) float gs[kDcKC];
+  // double-buffered staging: chunk c+1 streams in (cp.async, no registers, no waiting) while chunk c is computed
+  __shared__ __align__(16) float xs[2][G::XS_PADDED];
+  __shared__ __align__(16) float gs[2][kDcKC];
   __shared__ __align__(16) float red[kDcWarps][G::TILE];
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -79,58 +85,71 @@ __global__ void __launch_bounds__(kDcThreads) dconv_fir_kernel(DconvArgs a) {
 #pragma unroll
   for (int i = 0; i < TN; i++) acc[i] = 0.f;
 
-  for (int k0 = k_lo; k0 < k_hi; k0 += kDcKC) {
-    // ---- stage xl[t0 + k0, +XS) and g[k0, +KC) -------------------------------------------------------
+  // ---- stage xl[t0 + k0, +XS) and g[k0, +KC) into buffer b ------------------------------------------------
+  auto stage = [&](int b, int k0) {
     if (a.vec_ok) {
+      const uint32_t xs_s = (uint32_t)__cvta_generic_to_shared(&xs[b][0]), gs_s = (uint32_t)__cvta_generic_to_shared(&gs[b][0]);
       for (int i = tid * 4; i < G::XS; i += kDcThreads * 4) {
-        const int xi = t0 + k0 + i;  // multiple of 4; irsize % 4 == 0, so a float4 never straddles the seam
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xi < total) v = xi < irsize ? *reinterpret_cast<const float4 *>(hist + xi)
-                                        : *reinterpret_cast<const float4 *>(in + (xi - irsize));
-        *reinterpret_cast<float4 *>(xs + G::xi(i)) = v;
+        const int xi = t0 + k0 + i;  // multiple of 4; irsize % 4 == 0, so 16 bytes never straddle the seam
+        const float *src = xi < irsize ? hist + xi : in + (xi - irsize);
+        const int nbytes = xi < total ? 16 : 0;  // 0: zero fill
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xs_s + (uint32_t)G::xi(i) * 4u),
+                     "l"(nbytes ? src : hist), "r"(nbytes)
+                     : "memory");
       }
       for (int i = tid * 4; i < kDcKC; i += kDcThreads * 4) {
-        const int k = k0 + i;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k + 3 < k_hi) {
-          v = *reinterpret_cast<const float4 *>(grev + k);
-        } else {
-          if (k < k_hi) v.x = grev[k];
-          if (k + 1 < k_hi) v.y = grev[k + 1];
-          if (k + 2 < k_hi) v.z = grev[k + 2];
-        }
-        *reinterpret_cast<float4 *>(gs + i) = v;
+        const int k = k0 + i;  // k_hi is a multiple of 4 here: a group of four taps is all inside or all outside
+        const int nbytes = k < k_hi ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(gs_s + (uint32_t)i * 4u),
+                     "l"(nbytes ? grev + k : grev), "r"(nbytes)
+                     : "memory");
       }
     } else {
       for (int i = tid; i < G::XS; i += kDcThreads) {
         const int xi = t0 + k0 + i;
         float v = 0.f;
         if (xi < total) v = xi < irsize ? hist[xi] : in[xi - irsize];
-        xs[G::xi(i)] = v;
+        xs[b][G::xi(i)] = v;
       }
       for (int i = tid; i < kDcKC; i += kDcThreads) {
         const int k = k0 + i;
-        gs[i] = k < k_hi ? grev[k] : 0.f;
+        gs[b][i] = k < k_hi ? grev[k] : 0.f;
       }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  stage(0, k_lo);
+  int buf = 0;
+  for (int k0 = k_lo; k0 < k_hi; k0 += kDcKC, buf ^= 1) {
+    if (k0 + kDcKC < k_hi) {
+      stage(buf ^ 1, k0 + kDcKC);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     // ---- this warp's slice of the chunk: TN outputs per lane, 8 taps per step ----------------------------
     const int kw = warp * kDcWarpTaps;
     if (k0 + kw < k_hi) {  // warp-uniform: skip slices that are all padding
       const int xb = lane * TN + kw;  // logical index of this lane's first window element
+      // xb is a multiple of TN, so xi(xb + r) == xi(xb) + xi(r): one base register, every window load below
+      // addresses it with a compile-time offset (no index arithmetic in the unrolled loop)
+      const float *xwb = &xs[buf][0] + G::xi(xb);
+      const float *gwb = &gs[buf][0] + kw;
       float xw[TN + 8];
 #pragma unroll
       for (int i = 0; i < TN; i += 4) {
-        const float4 v = *reinterpret_cast<const float4 *>(xs + G::xi(xb + i));
+        const float4 v = *reinterpret_cast<const float4 *>(xwb + G::xi(i));
         xw[i] = v.x, xw[i + 1] = v.y, xw[i + 2] = v.z, xw[i + 3] = v.w;
       }
 #pragma unroll
       for (int kk = 0; kk < kDcWarpTaps; kk += 8) {  // fully unrolled: the sliding window never moves registers
-        const float4 v2 = *reinterpret_cast<const float4 *>(xs + G::xi(xb + kk + TN)),
-                     v3 = *reinterpret_cast<const float4 *>(xs + G::xi(xb + kk + TN + 4));
+        const float4 v2 = *reinterpret_cast<const float4 *>(xwb + G::xi(kk + TN)),
+                     v3 = *reinterpret_cast<const float4 *>(xwb + G::xi(kk + TN + 4));
         xw[TN] = v2.x, xw[TN + 1] = v2.y, xw[TN + 2] = v2.z, xw[TN + 3] = v2.w;
         xw[TN + 4] = v3.x, xw[TN + 5] = v3.y, xw[TN + 6] = v3.z, xw[TN + 7] = v3.w;
-        const float4 g0 = *reinterpret_cast<const float4 *>(gs + kw + kk), g1 = *reinterpret_cast<const float4 *>(gs + kw + kk + 4);
+        const float4 g0 = *reinterpret_cast<const float4 *>(gwb + kk), g1 = *reinterpret_cast<const float4 *>(gwb + kk + 4);
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -140,7 +159,7 @@ __global__ void __launch_bounds__(kDcThreads) dconv_fir_kernel(DconvArgs a) {
         for (int i = 0; i < TN; i++) xw[i] = xw[i + 8];
       }
     }
-    __syncthreads();
+    __syncthreads();  // buffer `buf` is restaged by the next iteration
   }
 
   // ---- reduce the warps' tap slices ------------------------------------------------------------------------

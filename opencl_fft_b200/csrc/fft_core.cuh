@@ -27,9 +27,11 @@ namespace b2f {
 // FMUL2 / FFMA2). An interleaved complex value IS such a pair, and the SASS operands take free modifiers -- lane
 // swap (.LO_HI), per-lane negate (.NP), scalar broadcast (.F32) -- which ptxas folds from the mov.b64 pack /
 // unpack below. So a complex add is ONE instruction, a quarter turn folded into the following add costs none, a
-// complex multiply is two (FMUL2 + FFMA2). The FP32 pipe spends the same cycles as with scalar code (FFMA2 issues
-// every other cycle per scheduler, tools/pk_probe.cu), but the instruction count of a radix-16 pass halves,
-// which is what large transforms are bound by. -DB2F_PACKED=0 builds the scalar forms.
+// complex multiply is two (FMUL2 + FFMA2): the FP instruction count of a radix-16 pass halves (cfft_kernel<12>:
+// 920 -> 608 SASS instructions). Measured effect on B200: none either way (tools/pk_probe.cu: an FFMA2 occupies
+// pipe AND issue port like two FFMAs; every FFT size times the same within 1 %), which also shows that these
+// kernels are not bound by instruction issue. Kept because the code is smaller; -DB2F_PACKED=0 builds the scalar
+// forms.
 #ifndef B2F_PACKED
 #define B2F_PACKED 1
 #endif
