@@ -35,6 +35,10 @@ namespace b2f {
 #ifndef B2F_PACKED
 #define B2F_PACKED 1
 #endif
+// 1: pass twiddles W^(r k) for r not a power of two are derived by multiplication instead of loaded (fft_pass)
+#ifndef B2F_TW_DERIVE
+#define B2F_TW_DERIVE 1
+#endif
 typedef unsigned long long b2f_u64;
 __device__ __forceinline__ b2f_u64 pk2(float lo, float hi) {
   b2f_u64 r;
@@ -218,12 +222,32 @@ __device__ __forceinline__ void fft_pass(Load &load, Store &store, float2 *sm, c
     const int j = t + q * T;
     const int k = j & (NS - 1);
     if constexpr (!FIRST) {
+#if B2F_TW_DERIVE
+      // Row r of the table holds W^(r k): only the power-of-two rows are LOADED, the others are products of two
+      // of them (r = hi + lo, hi the top bit; at most three roundings deep for r = 15, ~2e-7). The loads go
+      // through the same LSU data pipe as the shared-memory exchanges, which is the SM-side limit of these
+      // kernels (ncu: 76-82 % busy at full HBM rate with all R-1 rows loaded); the FP32 pipe has the headroom.
+      float2 wr[R];
+#pragma unroll
+      for (int r = 1; r < R; r <<= 1) {
+        wr[r] = TW_SMEM ? tw[TWO + (r - 1) * NS + k] : __ldg(&tw[TWO + (r - 1) * NS + k]);
+        if constexpr (INV) wr[r].y = -wr[r].y;
+      }
+#pragma unroll
+      for (int r = 3; r < R; r++) {
+        const int hi = r >= 8 ? 8 : (r >= 4 ? 4 : 2);
+        if (r != hi) wr[r] = cmul(wr[hi], wr[r - hi]);
+      }
+#pragma unroll
+      for (int r = 1; r < R; r++) v[q][r] = cmul(v[q][r], wr[r]);
+#else
 #pragma unroll
       for (int r = 1; r < R; r++) {
         float2 w = TW_SMEM ? tw[TWO + (r - 1) * NS + k] : __ldg(&tw[TWO + (r - 1) * NS + k]);
         if constexpr (INV) w.y = -w.y;
         v[q][r] = cmul(v[q][r], w);
       }
+#endif
     }
     dftR<R, INV>(v[q]);
     const int base = (j - k) * R + k;  // (j / NS) * NS * R + k
