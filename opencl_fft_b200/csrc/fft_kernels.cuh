@@ -133,6 +133,20 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
 // so that   out_i = hs*S + hw*D,  out_j = conj(hs*S - hw*D),  S = A + conj(B), D = conj(B) - A,
 // the same algebra as the reference's conv/iconv kernels (cl_fft.cpp:178-205), 12 instructions per pair.
 // =====================================================================================================
+// folded split twiddle of element t + m*T, T = N/16, from the one of element t: w2[t + m*T] = w2[t] * exp(-+ i pi m/16),
+// a compile-time constant per m (one table load per thread instead of eight; the loads share the LSU data pipe with
+// the shared-memory exchanges, the multiplies go to the idle FP32 pipe)
+template <bool INV>
+__device__ __forceinline__ float2 split_tw(float2 hw0, int m) {
+  constexpr float kC[8] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                           0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                           0.19509032201612826785f};
+  constexpr float kS[8] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                           0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                           0.98078528040323044913f};
+  return m == 0 ? hw0 : cmulc<INV>(hw0, kC[m], kS[m]);
+}
+
 template <int LOGN>
 struct RegSplitGeom {
   using G = FftGeom<LOGN>;
@@ -167,6 +181,10 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   if (!active) return;
   const int pt = (t == 0) ? 0 : T - t;  // partner thread (itself for t = 0 and t = T/2)
   const float hs = 0.5f * scale;
+  // measured: deriving the split twiddles pays up to N = 4096 (r2c 4096: 89 -> 92 % of the HBM peak); above, the
+  // 512- and 1024-thread CTAs are bound by their phases, not by the LSU pipe, and the table loads are faster
+  constexpr bool DERIVE = LOGN <= 12;
+  const float2 hw0 = __ldg(&hw[t]);
 #pragma unroll
   for (int m = 0; m < 8; m++) {
     if (m == 0 && t == 0) {
@@ -176,7 +194,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
     }
     const int pm = (t == 0) ? 16 - m : 15 - m;
     float2 a = x[m], bb = sm[(pm - 8) * T + pt];
-    rfft_pair_folded<false>(a, bb, __ldg(&hw[t + m * T]), hs);
+    rfft_pair_folded<false>(a, bb, DERIVE ? split_tw<false>(hw0, m) : __ldg(&hw[t + m * T]), hs);
     __stcs(dst + t + m * T, a);
     __stcs(dst + pt + pm * T, bb);
   }
@@ -214,7 +232,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
       x[0] = make_float2(x[0].x + x[0].y, x[0].x - x[0].y);  // packed (DC, Nyquist); hi[0] = element N/2 passes through
       continue;
     }
-    rfft_pair_folded<true>(x[m], hi[m], __ldg(&hw[t + m * T]), 0.5f);
+    rfft_pair_folded<true>(x[m], hi[m], __ldg(&hw[t + m * T]), 0.5f);  // (derived twiddles measured slower here)
   }
   // the one exchange: hand the high members to their owners
 #pragma unroll
