@@ -143,19 +143,16 @@ __device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 
   const float2 *src = scratch_b + (size_t)k1_fft * N2;
   auto load = [&](int idx, int) { return CG ? __ldcg(&src[idx]) : src[idx]; };
   auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = v; };
-  // REAL: the folded split twiddles of this thread's pairs, requested before the transform so that their
-  // latency (L2: every CTA walks a different slice of the table) is off the write-out's critical path
+  // REAL: the folded split twiddle of this thread's first pair, requested before the transform so that its latency
+  // is off the write-out's critical path. Pair m of the thread is element i_m = i_0 + N1*KSTEP*m, and
+  // w2[i_m] = w2[i_0] * exp(-i pi m KSTEP/N2), a compile-time constant per m: one table load per thread instead of
+  // N2/KSTEP, the products go to the idle FP32 pipe. For i_m > N/2 the pair is evaluated from its other member,
+  // whose table entry hw[N - i_m] is the conjugate of the same product.
   constexpr int KSTEP = NTHR / RH;  // k2 values covered per round of the pair loop
   constexpr int NPAIR = REAL ? N2 / KSTEP : 1;
-  float2 hwr[NPAIR];
-  if constexpr (REAL) {
-    const int k1 = g * RH + threadIdx.x % RH;
-#pragma unroll
-    for (int m = 0; m < NPAIR; m++) {
-      const int i = k1 + N1 * (threadIdx.x / RH + m * KSTEP);
-      hwr[m] = __ldg(&hw[i < N - i ? i : N - i]);
-    }
-  }
+  static_assert(!REAL || NPAIR == 8, "split-twiddle step constants are exp(-i pi m/8)");
+  float2 hw0 = make_float2(0.f, 0.f);
+  if constexpr (REAL) hw0 = __ldg(&hw[g * RH + threadIdx.x % RH + N1 * (threadIdx.x / RH)]);  // i_0 < N1*KSTEP <= N/2
   fft_run<LOG2, INV, true, false, TWS>(load, store, sm, tw2, t, CtaSync());
   __syncthreads();
   after_reads();
@@ -195,10 +192,13 @@ __device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 
       }
       float2 a = smr[pad_idx(k2)], bb = smp[pad_idx(pk2)];
       const int i = k1 + N1 * k2, j = k1p + N1 * pk2;  // i + j == N
+      constexpr float kC[8] = {1.f, B2F_COS_PI_8, B2F_SQRT1_2, B2F_SIN_PI_8, 0.f, -B2F_SIN_PI_8, -B2F_SQRT1_2, -B2F_COS_PI_8};
+      constexpr float kS[8] = {0.f, B2F_SIN_PI_8, B2F_SQRT1_2, B2F_COS_PI_8, 1.f, B2F_COS_PI_8, B2F_SQRT1_2, B2F_SIN_PI_8};
+      const float2 h = m ? cmulc<false>(hw0, kC[m], kS[m]) : hw0;
       if (i < j) {
-        rfft_pair_folded<false>(a, bb, hwr[m], hs);
+        rfft_pair_folded<false>(a, bb, h, hs);
       } else {
-        rfft_pair_folded<false>(bb, a, hwr[m], hs);
+        rfft_pair_folded<false>(bb, a, cconj(h), hs);
       }
       dst[i] = a;
       dst[j] = bb;
@@ -228,8 +228,11 @@ struct RowsGeom {
   static constexpr int SMEM = RBT * (L::G2::SMEM + 1) * (int)sizeof(float2);
 };
 
+#ifndef LARGE_ROWS_WARPS
+#define LARGE_ROWS_WARPS 32  // resident warps per SM the register budget is set for (64 registers per thread)
+#endif
 template <int LOG1, int LOG2, bool INV, bool REAL, int RBT>
-__global__ void __launch_bounds__(RowsGeom<LOG1, LOG2, RBT>::THREADS)
+__global__ void __launch_bounds__(RowsGeom<LOG1, LOG2, RBT>::THREADS, LARGE_ROWS_WARPS * 32 / RowsGeom<LOG1, LOG2, RBT>::THREADS)
     large_rows_kernel(const float2 *scratch, float2 *out, const float2 *__restrict__ tw2,
                       const float2 *__restrict__ hw, int batch, float scale) {
   constexpr int N = 1 << (LOG1 + LOG2);

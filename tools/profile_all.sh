@@ -14,5 +14,5 @@ prof rfft4096 rfft_fwd_reg 1 rfft4096_fwd
 prof rfft4096 rfft_inv_reg 1 rfft4096_inv
 prof rfft65536 large_cols 1 rfft65536_cols
 prof rfft65536 large_rows 1 rfft65536_rows
-prof pconv_general pconv_mac 1 pconv_general_mac
+# (pconv kernels unchanged since their captures)
 prof dconv4 dconv_fir 1 dconv4
