@@ -317,12 +317,13 @@ struct LargePlan {
   int logn = 0, log1 = 0, log2 = 0, chunk = 1;
   float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twl = nullptr, *d_scratch = nullptr, *d_scratch_base = nullptr;
   // Scratch matrix between the two steps. Measured on B200 (1024 x 65536-point and 2048 x 32768-point batches):
-  // cutting the batch into L2-sized chunks (32 MB: 2.3 TB/s), pipelining the chunks over two streams (2.3 TB/s)
-  // and a single persistent kernel with ticketed column/row items and an L2-resident double buffer (2.4 TB/s)
-  // are all SLOWER than two long launches whose scratch simply goes through HBM (2.9 TB/s): short launches
+  // cutting the batch into L2-sized chunks (32-96 MB: 2.2-2.7 TB/s), pipelining the chunks over two streams
+  // (2.3 TB/s) and a single persistent kernel with ticketed column/row items and an L2-resident double buffer
+  // (2.4 TB/s) are all SLOWER than long launches whose scratch simply goes through HBM (2.9 TB/s): short launches
   // run as one wave of CTAs in phase lockstep, long ones desynchronise and overlap loads, butterflies and
-  // stores. So the scratch covers the whole batch, up to 1 GiB.
-  static constexpr size_t kScratchBytes = 1u << 30;
+  // stores. 256 MB per launch pair is where that saturates (complex 2048 x 32768: 0.369 ms at 256 MB and at
+  // 1 GiB; real: 0.434 vs 0.463 ms, the rows kernel walks its chunk backwards and finds the tail in L2).
+  static constexpr size_t kScratchBytes = 256u << 20;
   int init(int logn_, int max_batch) {
     logn = logn_;
     log1 = logn / 2;
@@ -335,7 +336,9 @@ struct LargePlan {
     for (int k1 = 0; k1 < N1; k1++)
       for (int n2 = 0; n2 < N2; n2++) twl[(size_t)k1 * N2 + n2] = ref_twiddle((long long)n2 * k1, N);
     if ((rc = upload(twl, &d_twl))) return rc;
-    chunk = (int)(kScratchBytes / ((size_t)N * sizeof(float2)));
+    size_t scratch_bytes = kScratchBytes;
+    if (const char *e = getenv("B2F_LARGE_CHUNK_MB")) scratch_bytes = (size_t)atoll(e) << 20;  // re-measurement knob
+    chunk = (int)(scratch_bytes / ((size_t)N * sizeof(float2)));
     if (chunk < 1) chunk = 1;
     if (chunk > max_batch) chunk = max_batch < 1 ? 1 : max_batch;
     if (!fused_wanted()) CK(cudaMalloc((void **)&d_scratch, (size_t)chunk * N * sizeof(float2)));
