@@ -349,12 +349,15 @@ struct LargePlan {
       if (p) cudaFree(p);
     d_tw1 = d_tw2 = d_twl = d_scratch = d_fscratch = nullptr;
   }
-  template <int L1, int L2, bool INV, bool REAL, int RBT>
+  // UNSPLIT: inverse real transform, the unsplit fused into the columns kernel (hw = folded inverse split table)
+  template <int L1, int L2, bool INV, bool REAL, int RBT, bool UNSPLIT = false>
   int run_tt(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw) {
     using L = LargeGeom<L1, L2>;
     using R = RowsGeom<L1, L2, RBT>;
+    static_assert(!UNSPLIT || (INV && !REAL), "the fused unsplit precedes an inverse complex transform");
     int rc;
     if ((rc = set_smem(large_cols_kernel<L1, L2, INV>, L::SMEM_A))) return rc;
+    if (UNSPLIT && (rc = set_smem(large_cols_unsplit_kernel<L1, L2>, L::SMEM_A))) return rc;
     if ((rc = set_smem(large_rows_kernel<L1, L2, INV, REAL, RBT>, R::SMEM))) return rc;
     for (int b0 = 0; b0 < batch; b0 += chunk) {
       const int nb = batch - b0 < chunk ? batch - b0 : chunk;
@@ -365,7 +368,10 @@ struct LargePlan {
       if (gyb > nb) gyb = nb;
       const float2 *src = in + (size_t)b0 * L::N;
       float2 *dst = out + (size_t)b0 * L::N;
-      large_cols_kernel<L1, L2, INV><<<dim3(gxa, gya), L::THREADS, L::SMEM_A, st>>>(src, d_scratch, d_tw1, d_twl, nb);
+      if constexpr (UNSPLIT)
+        large_cols_unsplit_kernel<L1, L2><<<dim3(gxa, gya), L::THREADS, L::SMEM_A, st>>>(src, d_scratch, d_tw1, d_twl, hw, nb);
+      else
+        large_cols_kernel<L1, L2, INV><<<dim3(gxa, gya), L::THREADS, L::SMEM_A, st>>>(src, d_scratch, d_tw1, d_twl, nb);
       CK(cudaGetLastError());
       large_rows_kernel<L1, L2, INV, REAL, RBT><<<dim3(gxb, gyb), R::THREADS, R::SMEM, st>>>(d_scratch, dst, d_tw2, hw, nb, scale);
       CK(cudaGetLastError());
@@ -445,6 +451,10 @@ struct LargePlan {
       if (fused_wanted()) return run_fused_t<7, 8, false, true>(in, out, batch, fwd_scale, st, hw);
       if (logn == 15) return run_t<7, 8, false, true>(in, out, batch, fwd_scale, st, hw);
       if (logn == 16) return run_t<8, 8, false, true>(in, out, batch, fwd_scale, st, hw);
+    }
+    if (inv && !getenv("B2F_SEPARATE_SPLIT") && !fused_wanted()) {  // inverse: unsplit fused into the columns kernel
+      if (logn == 15) return run_tt<7, 8, true, false, LargeGeom<7, 8>::RB, true>(in, out, batch, 1.0f, st, hw);
+      if (logn == 16) return run_tt<8, 8, true, false, LargeGeom<8, 8>::RB, true>(in, out, batch, 1.0f, st, hw);
     }
     const long long pairs = (long long)batch * (N / 2);
     const int grid = (int)((pairs + 255) / 256);

@@ -106,6 +106,85 @@ __global__ void __launch_bounds__(256, LARGE_COLS_MINB)
   }
 }
 
+// Inverse real transform: the unsplit of cl_fft.cpp:192-205 fused into the columns kernel. The partner of element
+// (n1, n2) is (N1-1-n1, N2-n2) [(N1-n1, 0) in column 0], so a CTA owns C/2 columns {g*C/2 ...} and their mirrors
+// {N2 - n2} (column 0 mirrors itself; its slot hosts column N2/2, which also pairs with itself): the whole tile is
+// staged in shared memory, every pair is unsplit there once, then the column transforms run in place.
+// grid = (N2 / C, batch slots). hw: folded inverse table (conj(0.5 i w2)), N/2 + 1 entries.
+template <int LOG1, int LOG2>
+__global__ void __launch_bounds__(256, 2)
+    large_cols_unsplit_kernel(const float2 *in, float2 *scratch, const float2 *__restrict__ tw1,
+                              const float2 *__restrict__ twl, const float2 *__restrict__ hw, int batch) {
+  using L = LargeGeom<LOG1, LOG2>;
+  constexpr int N1 = L::N1, N2 = L::N2, N = L::N, C = L::C, CH = C / 2, E = L::G1::E, T = L::G1::T;
+  constexpr int RSTEP = 256 / CH, NPAIR = N1 / RSTEP;  // rows per round of the pair loop, rounds
+  extern __shared__ float2 smem[];
+  const int c = threadIdx.x % C, t = threadIdx.x / C, g = blockIdx.x;
+  auto col_of = [&](int slot) -> int {
+    if (slot < CH) return g * CH + slot;
+    const int d = g * CH + (slot - CH);
+    return d == 0 ? N2 / 2 : N2 - d;
+  };
+  const int n2 = col_of(c);
+  float2 *smc = smem + c * L::G1::SMEM;
+  float2 wreg[E];
+  large_cols_twiddles<LOG1, LOG2, true>(wreg, twl, n2, t);
+  // pair duty of this thread: direct column cd, rows n1 = r0 + RSTEP*m
+  const int cd = threadIdx.x % CH, r0 = threadIdx.x / CH;
+  const int n2d = g * CH + cd;
+  const bool col0 = (n2d == 0);
+  float2 *smd = smem + cd * L::G1::SMEM, *smm = smem + (cd + CH) * L::G1::SMEM;
+  // split twiddle of the thread's first pair; pair m is element i_0 + N2*RSTEP*m and
+  // w2[i_m] = w2[i_0] * exp(+i pi m RSTEP/N1) = w2[i_0] * exp(+i pi m/8): one table load for the whole launch
+  static_assert(N1 / RSTEP == 8, "split-twiddle step constants are exp(i pi m/8)");
+  const float2 hw0 = __ldg(&hw[N2 * r0 + n2d]);  // i_0 < N/8
+  constexpr float kC[8] = {1.f, B2F_COS_PI_8, B2F_SQRT1_2, B2F_SIN_PI_8, 0.f, -B2F_SIN_PI_8, -B2F_SQRT1_2, -B2F_COS_PI_8};
+  constexpr float kS[8] = {0.f, B2F_SIN_PI_8, B2F_SQRT1_2, B2F_COS_PI_8, 1.f, B2F_COS_PI_8, B2F_SQRT1_2, B2F_SIN_PI_8};
+  for (int b = blockIdx.y; b < batch; b += gridDim.y) {
+    const float2 *src = in + (size_t)b * N;
+#pragma unroll
+    for (int s = 0; s < E; s++) smc[pad_idx(t + s * T)] = src[(size_t)(t + s * T) * N2 + n2];
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < NPAIR; m++) {
+      const int n1 = r0 + RSTEP * m;
+      const float2 h = m ? cmulc<true>(hw0, kC[m], kS[m]) : hw0;  // entry i_m of the table, extended past N/2
+      if (!col0) {
+        float2 a = smd[pad_idx(n1)], bb = smm[pad_idx(N1 - 1 - n1)];
+        const int i = N2 * n1 + n2d;
+        if (i < N - i) {
+          rfft_pair_folded<true>(a, bb, h, 0.5f);
+        } else {
+          rfft_pair_folded<true>(bb, a, cconj(h), 0.5f);  // hw[N - i] == conj(h)
+        }
+        smd[pad_idx(n1)] = a;
+        smm[pad_idx(N1 - 1 - n1)] = bb;
+      } else if (n1 < N1 / 2) {
+        // column 0: (n1, 0) <-> (N1 - n1, 0); element 0 is the packed (DC, Nyquist), element N/2 passes through (Q3)
+        if (n1 == 0) {
+          smd[pad_idx(0)] = rfft_dc<true>(smd[pad_idx(0)]);
+        } else {
+          float2 a = smd[pad_idx(n1)], bb = smd[pad_idx(N1 - n1)];
+          rfft_pair_folded<true>(a, bb, h, 0.5f);
+          smd[pad_idx(n1)] = a;
+          smd[pad_idx(N1 - n1)] = bb;
+        }
+        // column N2/2 (hosted in column 0's mirror slot): (n1, N2/2) <-> (N1 - 1 - n1, N2/2)
+        float2 a = smm[pad_idx(n1)], bb = smm[pad_idx(N1 - 1 - n1)];
+        rfft_pair_folded<true>(a, bb, __ldg(&hw[N2 * n1 + N2 / 2]), 0.5f);
+        smm[pad_idx(n1)] = a;
+        smm[pad_idx(N1 - 1 - n1)] = bb;
+      }
+    }
+    __syncthreads();
+    float2 *dst = scratch + (size_t)b * N + n2;
+    auto load = [&](int idx, int) { return smc[pad_idx(idx)]; };
+    auto store = [&](int idx, float2 v, int slot) { dst[(size_t)idx * N2] = cmul(v, wreg[slot]); };
+    fft_run<LOG1, true, false, true>(load, store, smc, tw1, t, CtaSync());
+    __syncthreads();  // shared memory is reused by the next transform
+  }
+}
+
 // grid = (N1 / RB, batch slots). Reads scratch rows, writes out[k1 + N1*k2] * scale.
 // REAL (forward real transform): the split of cl_fft.cpp:178-191 is fused into the write-out. A CTA then
 // owns 8 rows {8g..8g+7} and their mirrors {N1-k} (row 0 mirrors itself; its slot hosts row N1/2), so both
