@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libb200fft.so")
+LIB_PATH = os.environ.get("B2F_LIB_PATH") or os.path.join(_PKG, "lib", "libb200fft.so")  # (override: A/B builds)
 
 # every symbol include/b200fft.h declares: name -> (restype, argtypes)
 _vp, _i, _sz, _fp = C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_float)

@@ -284,6 +284,14 @@ __device__ __forceinline__ void fft_run(Load load, Store store, float2 *sm, cons
   if constexpr (S.npass > 3) fft_pass<LOGN, 3, INV, FIRST_INPLACE, LAST_INPLACE, TW_SMEM>(load, store, sm, tw, t, sync);
 }
 
+// input index read by thread t's value `slot` in the first pass (same arithmetic as fft_pass)
+template <int LOGN>
+__device__ __forceinline__ int first_pass_index(int t, int slot) {
+  using G = FftGeom<LOGN>;
+  constexpr int R = G::S.radix[0];
+  return t + (slot / R) * G::T + (slot % R) * (G::N / R);
+}
+
 // output index written by thread t's value `slot` in the last pass (same arithmetic as fft_pass)
 template <int LOGN>
 __device__ __forceinline__ int last_pass_index(int t, int slot) {

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256, LARGE_COLS_MINB)
     large_cols_kernel(const float2 *in, float2 *scratch, const float2 *__restrict__ tw1,
                       const float2 *__restrict__ twl, int batch) {
   using L = LargeGeom<LOG1, LOG2>;
-  constexpr int N2 = L::N2, N = L::N, C = L::C, E = L::G1::E;
+  constexpr int N = L::N, C = L::C, E = L::G1::E;
   extern __shared__ float2 smem[];
   const int c = threadIdx.x % C, t = threadIdx.x / C;
   const int n2 = blockIdx.x * C + c;
@@ -199,28 +199,35 @@ struct NoHook {
 // scratch has been consumed and before anything is written to `out`.
 // RBT: rows per CTA (RBT * T2 threads). REAL with RBT = 32 (16 direct rows + 16 mirrors) makes the direct members'
 // runs whole 128-byte lines (the mirrors' runs are 120 + 8 bytes); RBT = 16 gives 64-byte runs.
+// scratch row transformed by slot rr of row group g (REAL: RBT/2 direct rows, then their mirrors; row 0 mirrors
+// itself, its slot hosts row N1/2)
+template <int LOG1, bool REAL, int RBT>
+__device__ __forceinline__ int large_rows_k1(int g, int rr) {
+  constexpr int N1 = 1 << LOG1, RH = RBT / 2;
+  if (!REAL) return g * RBT + rr;
+  if (rr < RH) return g * RH + rr;
+  const int d = g * RH + (rr - RH);
+  return d == 0 ? N1 / 2 : N1 - d;
+}
+// PRE: the thread's first-pass inputs are already in `xin` (fetched during the previous transform's write-out)
 template <int LOG1, int LOG2, bool INV, bool REAL, bool CG, class Hook = NoHook, bool TWS = false,
-          int RBT = LargeGeom<LOG1, LOG2>::RB>
+          int RBT = LargeGeom<LOG1, LOG2>::RB, bool PRE = false>
 __device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 *out_b, float2 *smem,
                                                 const float2 *__restrict__ tw2, const float2 *__restrict__ hw,
-                                                float scale, int g, Hook after_reads = Hook()) {
+                                                float scale, int g, Hook after_reads = Hook(),
+                                                const float2 *xin = nullptr) {
   using L = LargeGeom<LOG1, LOG2>;
   constexpr int N1 = L::N1, N2 = L::N2, N = L::N, RB = RBT, T2 = L::G2::T, NTHR = RBT * T2, RH = RBT / 2;
   static_assert(!REAL || RB == 16 || RB == 32, "mirrored row groups are 8 + 8 or 16 + 16");
   const int t = threadIdx.x % T2, row = threadIdx.x / T2;
-  auto row_of = [&](int rr) -> int {
-    if (!REAL) return g * RB + rr;
-    if (rr < RH) return g * RH + rr;
-    const int d = g * RH + (rr - RH);
-    return d == 0 ? N1 / 2 : N1 - d;
-  };
+  auto row_of = [&](int rr) -> int { return large_rows_k1<LOG1, REAL, RBT>(g, rr); };
   // per-row stride in float2: odd when a half-warp reads one element from each of 16 rows, == 2 (mod 16) when it
   // reads two adjacent elements from each of 8 rows
   constexpr int RS = (REAL && RH == 8) ? L::ROWSTRIDE_R : L::ROWSTRIDE_C;
   float2 *sm = smem + row * RS;
   const int k1_fft = row_of(row);
   const float2 *src = scratch_b + (size_t)k1_fft * N2;
-  auto load = [&](int idx, int) { return CG ? __ldcg(&src[idx]) : src[idx]; };
+  auto load = [&](int idx, int slot) { return PRE ? xin[slot] : (CG ? __ldcg(&src[idx]) : src[idx]); };
   auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = v; };
   // REAL: the folded split twiddle of this thread's first pair, requested before the transform so that its latency
   // is off the write-out's critical path. Pair m of the thread is element i_m = i_0 + N1*KSTEP*m, and
@@ -307,19 +314,38 @@ struct RowsGeom {
   static constexpr int SMEM = RBT * (L::G2::SMEM + 1) * (int)sizeof(float2);
 };
 
+// Resident warps per SM the rows kernel's register budget is set for. Measured with the register prefetch of the
+// next transform (1024 x 65536 real / 32768 complex, ms): 32 warps (64 registers, spills) 0.263 / 0.186,
+// 24 warps 0.203 / 0.190, 16 warps (128 registers) 0.204 / 0.181; without the prefetch 0.219 / 0.187.
 #ifndef LARGE_ROWS_WARPS
-#define LARGE_ROWS_WARPS 32  // resident warps per SM the register budget is set for (64 registers per thread)
+#define LARGE_ROWS_WARPS 16
 #endif
 template <int LOG1, int LOG2, bool INV, bool REAL, int RBT>
 __global__ void __launch_bounds__(RowsGeom<LOG1, LOG2, RBT>::THREADS, LARGE_ROWS_WARPS * 32 / RowsGeom<LOG1, LOG2, RBT>::THREADS)
     large_rows_kernel(const float2 *scratch, float2 *out, const float2 *__restrict__ tw2,
                       const float2 *__restrict__ hw, int batch, float scale) {
-  constexpr int N = 1 << (LOG1 + LOG2);
+  using L = LargeGeom<LOG1, LOG2>;
+  constexpr int N = L::N, N2 = L::N2, T2 = L::G2::T, E = L::G2::E;
   extern __shared__ float2 smem[];
+  // The thread's 16 first-pass inputs of the NEXT transform are requested while the current one is being written
+  // out (their registers are free then): the scratch latency, a quarter of this kernel's stall samples when
+  // every transform started with a cold load, is off the critical path.
+  const float2 *row = scratch + (size_t)large_rows_k1<LOG1, REAL, RBT>(blockIdx.x, threadIdx.x / T2) * N2;
+  const int t = threadIdx.x % T2;
+  float2 xin[E];
+  auto fetch = [&](int b) {
+#pragma unroll
+    for (int s = 0; s < E; s++) xin[s] = row[(size_t)b * N + first_pass_index<LOG2>(t, s)];
+  };
   // last transform first: the tail of what the columns kernel has just written is still in the 126 MB L2
-  for (int b = batch - 1 - (int)blockIdx.y; b >= 0; b -= gridDim.y) {
-    large_rows_body<LOG1, LOG2, INV, REAL, false, NoHook, false, RBT>(scratch + (size_t)b * N, out + (size_t)b * N, smem,
-                                                                      tw2, hw, scale, blockIdx.x);
+  int b = batch - 1 - (int)blockIdx.y;
+  if (b >= 0) fetch(b);
+  for (; b >= 0; b -= gridDim.y) {
+    auto hook = [&]() {
+      if (b - (int)gridDim.y >= 0) fetch(b - (int)gridDim.y);
+    };
+    large_rows_body<LOG1, LOG2, INV, REAL, false, decltype(hook), false, RBT, true>(
+        scratch + (size_t)b * N, out + (size_t)b * N, smem, tw2, hw, scale, blockIdx.x, hook, xin);
     __syncthreads();
   }
 }
