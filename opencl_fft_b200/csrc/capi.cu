@@ -422,9 +422,8 @@ struct LargePlan {
     }
     const int ncl = batch < fused_clusters ? batch : fused_clusters;
     cfg.gridDim = dim3(8 * ncl, 1, 1);
-    static const int dbg = getenv("B2F_FUSED_DBG") ? atoi(getenv("B2F_FUSED_DBG")) : 0;  // timing experiments only
     CK(cudaLaunchKernelEx(&cfg, kern, in, out, d_fscratch, (const float2 *)d_tw1, (const float2 *)d_tw2,
-                          (const float2 *)d_twl, hw, batch, scale, dbg));
+                          (const float2 *)d_twl, hw, batch, scale));
     return B2F_OK;
   }
   template <int L1, int L2, bool INV, bool REAL>

@@ -383,7 +383,7 @@ template <int LOG1, int LOG2, bool INV, bool REAL, int MINB>
 __global__ void __launch_bounds__(256, MINB)
     large_fused_kernel(const float2 *in, float2 *out, float2 *scratch, const float2 *__restrict__ tw1,
                        const float2 *__restrict__ tw2, const float2 *__restrict__ twl,
-                       const float2 *__restrict__ hw, int batch, float scale, int dbg) {
+                       const float2 *__restrict__ hw, int batch, float scale) {
   using L = LargeGeom<LOG1, LOG2>;
   using F = FusedGeom<LOG1, LOG2>;
   constexpr int N1 = L::N1, N2 = L::N2, N = L::N, C = L::C, E = L::G1::E, S = 8;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(256, MINB)
         w = (slot & 3) ? cmul(wreg[slot >> 2], gpow[slot & 3]) : wreg[slot >> 2];
       else
         w = wreg[slot];
-      if (!(dbg & 4)) dst[(size_t)idx * N2] = cmul(v, w);
+      dst[(size_t)idx * N2] = cmul(v, w);
     };
     fft_run<LOG1, INV, false, false, true>(load, store, smc, stw1, t, CtaSync());
     __syncthreads();  // stage and work buffer are free again
@@ -461,18 +461,10 @@ __global__ void __launch_bounds__(256, MINB)
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   int bars = 0;  // barriers signalled so far; barrier j lives on xbar[j & 1], phase parity (j >> 1) & 1
   auto signal = [&]() {  // caller has just passed a __syncthreads() after the work being published
-    if (threadIdx.x < S) {
-      const uint32_t remote = tma::map_to_rank(xb0 + 8 * (bars & 1), threadIdx.x);
-      if (dbg & 1)
-        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-      else
-        tma::mbar_arrive_cluster_release(remote);
-    }
+    if (threadIdx.x < S) tma::mbar_arrive_cluster_release(tma::map_to_rank(xb0 + 8 * (bars & 1), threadIdx.x));
     bars++;
   };
-  auto wait_for = [&](int j) {
-    if (!(dbg & 2)) tma::mbar_wait(xb0 + 8 * (j & 1), (j >> 1) & 1);
-  };
+  auto wait_for = [&](int j) { tma::mbar_wait(xb0 + 8 * (j & 1), (j >> 1) & 1); };
 
   int b = cid, nb = cid + ncl, k = 0, j = 0;
   prefetch(b);
@@ -492,11 +484,8 @@ __global__ void __launch_bounds__(256, MINB)
     auto hook = [&]() {
       if (more) signal();
     };
-    if (!(dbg & 8))
-      large_rows_body<LOG1, LOG2, INV, REAL, true, decltype(hook), true>(scr + (size_t)k * N, out + (size_t)b * N, smem,
-                                                                         stw2, hw, scale, rank, hook);
-    else
-      hook();
+    large_rows_body<LOG1, LOG2, INV, REAL, true, decltype(hook), true>(scr + (size_t)k * N, out + (size_t)b * N, smem,
+                                                                       stw2, hw, scale, rank, hook);
     __syncthreads();
     if (!more) break;
     b = nb;

@@ -165,16 +165,21 @@ def test_device_pointer_api_matches_host_api(eng):
     assert torch.equal(d2, d_in)
 
 
-@pytest.mark.parametrize("cluster", [False, True])
+@pytest.mark.parametrize("path", ["default", "cluster", "fused", "fused3"])
 @pytest.mark.parametrize("batch", [1, 5, 71, 300])
-def test_large_fft_every_transform_of_a_batch(eng, batch, cluster, monkeypatch):
+def test_large_fft_every_transform_of_a_batch(eng, batch, path, monkeypatch):
     """The 65536-point real / 32768-point complex transforms: by default two long launches (columns, rows with
-    the real split fused); with B2F_CLUSTER_FFT=1 the single-pass kernel on 4-CTA clusters that exchange data
-    through distributed shared memory (a persistent cluster loops over several transforms when batch >
-    resident clusters). Check EVERY transform of the batch (a race shows up as a few wrong ones), twice, and
-    that the two runs agree bit for bit."""
-    if cluster:
+    the real split / unsplit fused); with B2F_CLUSTER_FFT=1 the single-pass kernel on 4-CTA clusters that exchange
+    data through distributed shared memory; with B2F_LARGE_FUSED=1 both steps in one launch on 8-CTA clusters with
+    L2-resident scratch and an mbarrier all-to-all per transform (a persistent cluster loops over several
+    transforms when batch > resident clusters). Check EVERY transform of the batch (a race shows up as a few
+    wrong ones), twice, and that the two runs agree bit for bit."""
+    if path == "cluster":
         monkeypatch.setenv("B2F_CLUSTER_FFT", "1")  # read when the plan is created
+    if path.startswith("fused"):
+        monkeypatch.setenv("B2F_LARGE_FUSED", "1")
+        if path == "fused3":
+            monkeypatch.setenv("B2F_FUSED_CLUSTERS", "3")  # few clusters: many transforms per cluster, all buffers reused
     size = 65536
     rng = np.random.default_rng(batch)
     x = rng.uniform(-1, 1, (batch, size)).astype(np.float32)
@@ -190,6 +195,12 @@ def test_large_fft_every_transform_of_a_batch(eng, batch, cluster, monkeypatch):
     want[:, 0] = (X[:, 0].real + 1j * X[:, size // 2].real) / size
     want[:, size // 4] = np.conj(want[:, size // 4])  # quirk Q3
     err = np.linalg.norm(outs[0] - want, axis=1) / np.linalg.norm(want, axis=1)
+    assert err.max() < 2e-6, (int(err.argmax()), float(err.max()))
+    # inverse real transform of every spectrum gives the signal back
+    inv = eng.Clrfft(0, size, False, max_batch=batch)
+    spec, back = outs[0].copy(), np.zeros((batch, size), np.float32)
+    assert inv.transform(spec.reshape(-1), back.reshape(-1)) == 0
+    err = np.linalg.norm(back - x, axis=1) / np.linalg.norm(x, axis=1)
     assert err.max() < 2e-6, (int(err.argmax()), float(err.max()))
     # complex path, forward and inverse, same kernel family
     z = (rng.uniform(-1, 1, (batch, size // 2)) + 1j * rng.uniform(-1, 1, (batch, size // 2))).astype(np.complex64)
