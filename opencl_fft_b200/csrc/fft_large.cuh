@@ -30,6 +30,18 @@
 #define LARGE_COLS_MINB 1  // measured: forcing 3 or 4 CTAs/SM (80/64 registers, spills) is 20-25 % slower
 #endif
 
+// Resident warps per SM the rows kernel's register budget is set for. Measured with the register prefetch of the
+// next transform (1024 x 65536 real / 32768 complex, ms): 32 warps (64 registers, spills) 0.263 / 0.186,
+// 24 warps 0.203 / 0.190, 16 warps (128 registers) 0.204 / 0.181; without the prefetch 0.219 / 0.187.
+#ifndef LARGE_ROWS_WARPS
+#define LARGE_ROWS_WARPS 16
+#endif
+#ifndef LARGE_ROWS_PAIR_UNROLL
+#define LARGE_ROWS_PAIR_UNROLL 8  // unroll of the real write-out's pair loop (8 = all pairs of a thread)
+#endif
+#define B2F_STR_(x) #x
+#define B2F_UNROLL(n) _Pragma(B2F_STR_(unroll n))
+
 namespace b2f {
 
 template <int LOG1, int LOG2>
@@ -262,7 +274,7 @@ __device__ __forceinline__ void large_rows_body(const float2 *scratch_b, float2 
     const float hs = 0.5f * scale;
     // rows 1..N1/2-1: all N2 values of k2, the pair's other member is on the mirror row.
     // row 0: pairs (0,k2) <-> (0,N2-k2) for k2 in [1, N2/2), plus the two self-paired elements.
-#pragma unroll
+    B2F_UNROLL(LARGE_ROWS_PAIR_UNROLL)
     for (int m = 0; m < NPAIR; m++) {
       const int k2 = threadIdx.x / RH + m * KSTEP;
       const int pk2 = zero ? N2 - k2 : N2 - 1 - k2;
@@ -314,12 +326,6 @@ struct RowsGeom {
   static constexpr int SMEM = RBT * (L::G2::SMEM + 1) * (int)sizeof(float2);
 };
 
-// Resident warps per SM the rows kernel's register budget is set for. Measured with the register prefetch of the
-// next transform (1024 x 65536 real / 32768 complex, ms): 32 warps (64 registers, spills) 0.263 / 0.186,
-// 24 warps 0.203 / 0.190, 16 warps (128 registers) 0.204 / 0.181; without the prefetch 0.219 / 0.187.
-#ifndef LARGE_ROWS_WARPS
-#define LARGE_ROWS_WARPS 16
-#endif
 template <int LOG1, int LOG2, bool INV, bool REAL, int RBT>
 __global__ void __launch_bounds__(RowsGeom<LOG1, LOG2, RBT>::THREADS, LARGE_ROWS_WARPS * 32 / RowsGeom<LOG1, LOG2, RBT>::THREADS)
     large_rows_kernel(const float2 *scratch, float2 *out, const float2 *__restrict__ tw2,
