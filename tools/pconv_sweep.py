@@ -59,6 +59,9 @@ def run(channels, cvs, pts, steps=100, tv=False):
     return row
 
 
+if len(sys.argv) == 4:  # one configuration: channels ir_taps partition
+    run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), steps=30)
+    sys.exit(0)
 rows = []
 for ch in (1, 8, 64, 512, 1024, 4096):
     rows.append(run(ch, 96000, 512))
