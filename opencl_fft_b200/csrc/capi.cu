@@ -799,12 +799,12 @@ static int launch_pconv_step_tt(const PconvArgs &a, int channels, int S, cudaStr
 }
 template <int LOGP, bool TV>
 static int launch_pconv_step_t(const PconvArgs &a, int channels, int S, cudaStream_t st) {
-  // Which MAC feeds the fused kernel: registers (128-bit loads, unrolled by 8) or the TMA ring. Measured on B200
-  // (256 channels x 480000 taps): pts 1024: 4.48 vs 6.02 TB/s, pts 2048: 4.14 vs 6.04 TB/s in favour of TMA;
-  // pts <= 512 (one tile per frame): 7.28 vs 6.88 TB/s in favour of registers; pts 4096 and few channels: registers.
-  // B2F_PCONV_TMA=0|1 forces one or the other.
+  // Which MAC feeds the fused kernel: registers (128-bit loads, 16 in flight per thread) or the TMA ring. Measured on
+  // B200 (256 channels x 480000 taps, TB/s, registers vs TMA): pts 512 7.28 vs 6.88; pts 1024 6.36 vs 6.03 (registers
+  // since the MAC walks each partition's whole frame at once); pts 2048 4.65 vs 6.07; pts 4096 4.09 vs 3.86 (4.43 at
+  // 1024 channels, where TMA wins). B2F_PCONV_TMA=0|1 forces one or the other.
   const char *force = getenv("B2F_PCONV_TMA");
-  const bool use_tma = force ? (force[0] == '1') : ((LOGP == 10 || LOGP == 11) && channels >= 64);
+  const bool use_tma = force ? (force[0] == '1') : ((LOGP == 11 && channels >= 64) || (LOGP == 12 && channels >= 512));
   return use_tma ? launch_pconv_step_tt<LOGP, TV, true>(a, channels, S, st)
                  : launch_pconv_step_tt<LOGP, TV, false>(a, channels, S, st);
 }

@@ -127,6 +127,45 @@ __device__ __forceinline__ void mac_segment(float4 &acc, float2 &acc0, const flo
   }
 }
 
+// The same for a frame wider than the CTA: TILES float4 per thread per frame (tile t at offset t*NT), walked
+// partition by partition so that the CTA reads every frame front to back in one go (two sequential streams per
+// CTA, as in the one-tile case) instead of sweeping all partitions once per tile with gaps of (TILES-1)/TILES of a
+// frame between its reads. 16 loads in flight per thread as above.
+template <int TILES, int NT>
+__device__ __forceinline__ void mac_segment_tiles(float4 (&acc)[TILES], float2 &acc0, const float4 *f, const float4 *g,
+                                                  int count, size_t stride4) {
+  constexpr int U = TILES >= 8 ? 1 : 8 / TILES;
+  int p = 0;
+  for (; p + U <= count; p += U) {
+    float4 a[U][TILES], b[U][TILES];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int t = 0; t < TILES; t++) {
+        a[u][t] = __ldcs(f + (size_t)(p + u) * stride4 + t * NT);
+        b[u][t] = __ldcs(g + (size_t)(p + u) * stride4 + t * NT);
+      }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int t = 0; t < TILES; t++) cmac2(acc[t], a[u][t], b[u][t]);
+      acc0.x += a[u][0].x * b[u][0].x;
+      acc0.y += a[u][0].y * b[u][0].y;
+    }
+  }
+  for (; p < count; p++) {
+#pragma unroll
+    for (int t = 0; t < TILES; t++) {
+      const float4 a = __ldcs(f + (size_t)p * stride4 + t * NT), b = __ldcs(g + (size_t)p * stride4 + t * NT);
+      cmac2(acc[t], a, b);
+      if (t == 0) {
+        acc0.x += a.x * b.x;
+        acc0.y += a.y * b.y;
+      }
+    }
+  }
+}
+
 struct PconvArgs {
   float2 *fdl;         // [channels][nparts][pts]
   float2 *irs;         // [channels][nparts][pts]
@@ -214,6 +253,91 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
   const int p_newg = TV ? a.wp2 : -1;
   const size_t stride4 = HALF;
 
+  if constexpr (!TMA && (P::TILES == 2 || P::TILES == 4)) {
+    // ---- register-fed, frame 2 or 4 times wider than the CTA: all tiles of a partition together (measured, 256
+    // channels x 480000 taps: pts 1024 4.48 -> 6.36 TB/s, pts 2048 4.14 -> 4.65; pts 4096 (8 tiles) 4.09 -> 3.78,
+    // so that size keeps the tile-by-tile sweep below) ------------------------------------------------------
+    constexpr int TL = P::TILES;
+    float4 acc[TL];
+#pragma unroll
+    for (int t = 0; t < TL; t++) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 acc0 = make_float2(0.f, 0.f);
+    const float4 *F = reinterpret_cast<const float4 *>(fdl) + tid;
+    const float4 *Gp = reinterpret_cast<const float4 *>(irs) + tid;
+    int p = p_lo;
+    while (p < p_hi) {
+      if (p == p_newx || p == p_newg) {
+        p++;
+        continue;
+      }
+      int end = p_hi;
+      if (p_newx > p && p_newx < end) end = p_newx;
+      if (p_newg > p && p_newg < end) end = p_newg;
+      const int wrap = nparts - rp;  // first p whose FDL frame index wraps to 0
+      if (wrap > p && wrap < end) end = wrap;
+      const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
+      mac_segment_tiles<TL, NT>(acc, acc0, F + (size_t)frame * stride4, Gp + (size_t)p * stride4, end - p, stride4);
+      p = end;
+    }
+#pragma unroll
+    for (int t = 0; t < TL; t++) {
+      const int q = t * NT + tid;
+      if (rank == 0) {
+        // the terms that involve frames produced by this launch, from shared memory
+        const int b0 = 2 * q;
+        float2 x0 = sX[pad_idx(b0)], x1 = sX[pad_idx(b0 + 1)];
+        float4 xn = make_float4(x0.x, x0.y, x1.x, x1.y);
+        float4 gn;
+        if (TV && p_newg == p_newx) {
+          float2 g0 = sG[pad_idx(b0)], g1 = sG[pad_idx(b0 + 1)];
+          gn = make_float4(g0.x, g0.y, g1.x, g1.y);
+        } else {
+          gn = __ldcs(Gp + t * NT + (size_t)p_newx * stride4);
+        }
+        cmac2(acc[t], xn, gn);
+        if (t == 0) {
+          acc0.x += xn.x * gn.x;
+          acc0.y += xn.y * gn.y;
+        }
+        if (TV && p_newg != p_newx) {
+          const int frame = (rp + p_newg < nparts) ? rp + p_newg : rp + p_newg - nparts;
+          float4 fo = __ldcs(F + t * NT + (size_t)frame * stride4);
+          float2 g0 = sG[pad_idx(b0)], g1 = sG[pad_idx(b0 + 1)];
+          float4 gg = make_float4(g0.x, g0.y, g1.x, g1.y);
+          cmac2(acc[t], fo, gg);
+          if (t == 0) {
+            acc0.x += fo.x * gg.x;
+            acc0.y += fo.y * gg.y;
+          }
+        }
+      }
+      if (q == 0) {  // packed (DC, Nyquist) bin: component-wise product
+        acc[t].x = acc0.x;
+        acc[t].y = acc0.y;
+      }
+      if (S > 1) sP[q] = acc[t];
+    }
+    if (S > 1) {
+      cluster.sync();  // all partials visible cluster-wide
+      if (rank == 0) {
+#pragma unroll
+        for (int t = 0; t < TL; t++) {
+          for (int r = 1; r < S; r++) {
+            const float4 o = cluster.map_shared_rank(sP, r)[t * NT + tid];
+            acc[t].x += o.x;
+            acc[t].y += o.y;
+            acc[t].z += o.z;
+            acc[t].w += o.w;
+          }
+        }
+      }
+      cluster.sync();  // remote reads done before anyone exits
+    }
+    if (rank == 0) {
+#pragma unroll
+      for (int t = 0; t < TL; t++) sP[HALF + t * NT + tid] = acc[t];  // parked; moved to sX after the barrier below
+    }
+  } else
   for (int tile = 0; tile < P::TILES; tile++) {
     const int q = tile * NT + tid;  // float4 index inside a frame: bins 2q, 2q+1
     const bool owns = worker && q < HALF;
