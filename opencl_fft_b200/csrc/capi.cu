@@ -195,14 +195,15 @@ static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *
     CK(cudaGetLastError());
     return B2F_OK;
   }
+  using BR = BatchGeom<LOGN, true>;  // generic real kernels (N < 128)
   if (inv) {
-    int rc = set_smem(rfft_inv_kernel<LOGN>, B::SMEM_BYTES);
+    int rc = set_smem(rfft_inv_kernel<LOGN>, BR::SMEM_BYTES);
     if (rc) return rc;
-    rfft_inv_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, w2, batch);
+    rfft_inv_kernel<LOGN><<<grid, BR::THREADS, BR::SMEM_BYTES, st>>>(in, out, tw, w2, batch);
   } else {
-    int rc = set_smem(rfft_fwd_kernel<LOGN>, B::SMEM_BYTES);
+    int rc = set_smem(rfft_fwd_kernel<LOGN>, BR::SMEM_BYTES);
     if (rc) return rc;
-    rfft_fwd_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, w2, batch, fwd_scale);
+    rfft_fwd_kernel<LOGN><<<grid, BR::THREADS, BR::SMEM_BYTES, st>>>(in, out, tw, w2, batch, fwd_scale);
   }
   CK(cudaGetLastError());
   return B2F_OK;
