@@ -34,7 +34,7 @@ B2F_HD constexpr Sched sched_for(int logn) {
     case 2: return {1, {4, 1, 1, 1}};
     case 3: return {1, {8, 1, 1, 1}};
     case 4: return {1, {16, 1, 1, 1}};
-    case 5: return {2, {16, 2, 1, 1}};
+    case 5: return {2, {8, 4, 1, 1}};
     case 6: return {2, {8, 8, 1, 1}};
     case 7: return {2, {8, 16, 1, 1}};
     case 8: return {2, {16, 16, 1, 1}};

@@ -13,7 +13,7 @@ import opencl_fft_b200 as eng  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--mb", type=int, default=512, help="input megabytes per launch (>> L2)")
 ap.add_argument("--iters", type=int, default=20)
-ap.add_argument("--logn-min", type=int, default=4)
+ap.add_argument("--logn-min", type=int, default=1)
 ap.add_argument("--logn-max", type=int, default=16)
 args = ap.parse_args()
 peak = 6544.7
