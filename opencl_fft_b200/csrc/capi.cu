@@ -816,7 +816,7 @@ static int launch_pconv_push_t(const float *ir, size_t stride, b2f_pconv *h, cud
   int rc = set_smem(pconv_push_ir_kernel<LOGP>, smem);
   if (rc) return rc;
   dim3 grid(h->nparts, h->channels, 1);
-  pconv_push_ir_kernel<LOGP><<<grid, P::NTHREADS, smem, st>>>(ir, stride, h->d_irs, h->d_tw, h->d_w2, h->nparts, h->wp2);
+  pconv_push_ir_kernel<LOGP><<<grid, P::FT, smem, st>>>(ir, stride, h->d_irs, h->d_tw, h->d_w2, h->nparts, h->wp2);
   CK(cudaGetLastError());
   return B2F_OK;
 }
