@@ -316,7 +316,7 @@ struct ClusterPlan {
 // ---- four-step plan for N > 2^kMaxSmemLogN ----------------------------------------------------------------
 struct LargePlan {
   int logn = 0, log1 = 0, log2 = 0, chunk = 1;
-  float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twl = nullptr, *d_scratch = nullptr, *d_scratch_base = nullptr;
+  float2 *d_tw1 = nullptr, *d_tw2 = nullptr, *d_twl = nullptr, *d_scratch = nullptr;
   // Scratch matrix between the two steps. Measured on B200 (1024 x 65536-point and 2048 x 32768-point batches):
   // cutting the batch into L2-sized chunks (32-96 MB: 2.2-2.7 TB/s), pipelining the chunks over two streams
   // (2.3 TB/s) and a single persistent kernel with ticketed column/row items and an L2-resident double buffer
