@@ -30,7 +30,10 @@ namespace b2f {
 
 namespace cg = cooperative_groups;
 
-constexpr int kDcWarps = 8;                    // warps per CTA; each takes a slice of the tap chunk
+#ifndef DCONV_WARPS
+#define DCONV_WARPS 8  // measured: 4 warps per CTA (half the cross-warp reduction per FMA) 44.0 TFLOP/s, 8 warps 57.0
+#endif
+constexpr int kDcWarps = DCONV_WARPS;          // warps per CTA; each takes a slice of the tap chunk
 constexpr int kDcThreads = kDcWarps * 32;
 constexpr int kDcKC = 1024;                    // taps staged per chunk
 constexpr int kDcWarpTaps = kDcKC / kDcWarps;  // taps per warp per chunk (multiple of 8)
