@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(BatchGeom<LOGN, true>::THREADS, BatchGeom<LOGN
 
 
 // =====================================================================================================
-// Register-level real transforms for N >= 128 (schedules whose first and last passes leave every thread
-// with the 16 values X[t + m*T], m = 0..15, T = N/16). The pair partner of element (t, m) is element
+// Register-level real transforms for N >= 64 (schedules whose first and last passes leave every thread
+// with the E = 16 (8 at N = 64) values X[t + m*T], m = 0..E-1, T = N/E; written below for E = 16). The pair partner of element (t, m) is element
 // (T - t, 15 - m) [(0, 16 - m) for t = 0], so the split / unsplit needs ONE partner thread: the two swap
 // half of their values through a small shared-memory staging area, each evaluates its 8 pairs once (the inverse
 // reads the partner's inputs from global memory instead and only hands the results over).
@@ -199,25 +199,27 @@ __global__ void __launch_bounds__(BatchGeom<LOGN, true>::THREADS, BatchGeom<LOGN
 // so that   out_i = hs*S + hw*D,  out_j = conj(hs*S - hw*D),  S = A + conj(B), D = conj(B) - A,
 // the same algebra as the reference's conv/iconv kernels (cl_fft.cpp:178-205), 12 instructions per pair.
 // =====================================================================================================
-// folded split twiddle of element t + m*T, T = N/16, from the one of element t: w2[t + m*T] = w2[t] * exp(-+ i pi m/16),
-// a compile-time constant per m (one table load per thread instead of eight; the loads share the LSU data pipe with
+// folded split twiddle of element t + m*T, T = N/E, from the one of element t: w2[t + m*T] = w2[t] * exp(-+ i pi m/E),
+// a compile-time constant per m (one table load per thread instead of E/2; the loads share the LSU data pipe with
 // the shared-memory exchanges, the multiplies go to the idle FP32 pipe)
-template <bool INV>
+template <bool INV, int E>
 __device__ __forceinline__ float2 split_tw(float2 hw0, int m) {
+  static_assert(E == 16 || E == 8, "");
   constexpr float kC[8] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
                            0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
                            0.19509032201612826785f};
   constexpr float kS[8] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
                            0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
                            0.98078528040323044913f};
-  return m == 0 ? hw0 : cmulc<INV>(hw0, kC[m], kS[m]);
+  const int k = m * (16 / E);  // angle pi m/E in units of pi/16
+  return m == 0 ? hw0 : cmulc<INV>(hw0, kC[k], kS[k]);
 }
 
 template <int LOGN>
 struct RegSplitGeom {
   using G = FftGeom<LOGN>;
   static constexpr Sched S = G::S;
-  static constexpr bool OK = (LOGN >= 7) && G::E == 16 && S.radix[S.npass - 1] == 16;
+  static constexpr bool OK = (LOGN >= 6) && (G::E == 16 || G::E == 8) && S.radix[S.npass - 1] == G::E;
   static constexpr int T = G::T;
   static constexpr int R0 = S.radix[0];
 };
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
     rfft_fwd_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
                         int batch, float scale) {
   using B = BatchGeom<LOGN>;
-  constexpr int N = 1 << LOGN, T = B::T;
+  constexpr int N = 1 << LOGN, T = B::T, E = FftGeom<LOGN>::E, H = E / 2;
   extern __shared__ float2 smem[];
   const int lt = threadIdx.x / T, t = threadIdx.x % T;
   const long long b = (long long)blockIdx.x * B::TPB + lt;
@@ -236,13 +238,13 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   const float2 *src = in + (active ? b : 0) * N;
   float2 *dst = out + (active ? b : 0) * N;
   float2 *sm = smem + lt * BatchGeom<LOGN>::ROW;
-  float2 x[16];
+  float2 x[E];
   auto load = [&](int idx, int) { return active ? __ldcs(src + idx) : make_float2(0.f, 0.f); };
   auto store = [&](int, float2 v, int slot) { x[slot] = v; };  // last pass: slot == m, value X[t + m*T]
   fft_run<LOGN, false>(load, store, sm, tw, t, CtaSync());
-  __syncthreads();  // every thread is past its last gather: sm becomes the staging area [8][T]
+  __syncthreads();  // every thread is past its last gather: sm becomes the staging area [E/2][T]
 #pragma unroll
-  for (int m = 8; m < 16; m++) sm[(m - 8) * T + t] = x[m];
+  for (int m = H; m < E; m++) sm[(m - H) * T + t] = x[m];
   __syncthreads();
   if (!active) return;
   const int pt = (t == 0) ? 0 : T - t;  // partner thread (itself for t = 0 and t = T/2)
@@ -252,15 +254,15 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   constexpr bool DERIVE = LOGN <= 12;
   const float2 hw0 = __ldg(&hw[t]);
 #pragma unroll
-  for (int m = 0; m < 8; m++) {
+  for (int m = 0; m < H; m++) {
     if (m == 0 && t == 0) {
       dst[0] = make_float2((x[0].x + x[0].y) * hs, (x[0].x - x[0].y) * hs);   // packed (DC, Nyquist)
-      dst[N / 2] = cscale(x[8], scale);               // never visited by the reference (Q3)
+      dst[N / 2] = cscale(x[H], scale);               // never visited by the reference (Q3)
       continue;
     }
-    const int pm = (t == 0) ? 16 - m : 15 - m;
-    float2 a = x[m], bb = sm[(pm - 8) * T + pt];
-    rfft_pair_folded<false>(a, bb, DERIVE ? split_tw<false>(hw0, m) : __ldg(&hw[t + m * T]), hs);
+    const int pm = (t == 0) ? E - m : E - 1 - m;
+    float2 a = x[m], bb = sm[(pm - H) * T + pt];
+    rfft_pair_folded<false>(a, bb, DERIVE ? split_tw<false, E>(hw0, m) : __ldg(&hw[t + m * T]), hs);
     __stcs(dst + t + m * T, a);
     __stcs(dst + pt + pm * T, bb);
   }
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
                         int batch) {
   using B = BatchGeom<LOGN>;
   using RS = RegSplitGeom<LOGN>;
-  constexpr int N = 1 << LOGN, T = B::T, R0 = RS::R0;
+  constexpr int N = 1 << LOGN, T = B::T, R0 = RS::R0, E = FftGeom<LOGN>::E, H = E / 2;
   extern __shared__ float2 smem[];
   const int lt = threadIdx.x / T, t = threadIdx.x % T;
   const long long b = (long long)blockIdx.x * B::TPB + lt;
@@ -283,17 +285,17 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   float2 *sm = smem + lt * BatchGeom<LOGN>::ROW;
   // a thread reads its 8 low members X[t + m*T] and, straight from global memory, their partners X[N - (t + m*T)]
   // (the values its partner thread will own): 16 loads as before, and no exchange before the unsplit
-  float2 x[16], hi[8];  // hi: unsplit high members, owned by the partner thread
+  float2 x[E], hi[H];  // hi: unsplit high members, owned by the partner thread
   const int pt = (t == 0) ? 0 : T - t;
   const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int m = 0; m < 8; m++) {
+  for (int m = 0; m < H; m++) {
     const int i = t + m * T;
     x[m] = active ? __ldcs(src + i) : zero2;
     hi[m] = active ? __ldcs(src + (i == 0 ? N / 2 : N - i)) : zero2;  // element N/2 rides with (t, m) = (0, 0)
   }
 #pragma unroll
-  for (int m = 0; m < 8; m++) {
+  for (int m = 0; m < H; m++) {
     if (m == 0 && t == 0) {
       x[0] = make_float2(x[0].x + x[0].y, x[0].x - x[0].y);  // packed (DC, Nyquist); hi[0] = element N/2 passes through
       continue;
@@ -302,17 +304,17 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   }
   // the one exchange: hand the high members to their owners
 #pragma unroll
-  for (int m = 0; m < 8; m++) {
-    const int pm = (t == 0) ? ((16 - m) & 15) : 15 - m;  // (t = 0, m = 0) parks element N/2 in slot 8
-    const int slot = (t == 0 && m == 0) ? 8 : pm;
-    sm[(slot - 8) * T + pt] = hi[m];
+  for (int m = 0; m < H; m++) {
+    const int pm = (t == 0) ? ((E - m) & (E - 1)) : E - 1 - m;  // (t = 0, m = 0) parks element N/2 in slot E/2
+    const int slot = (t == 0 && m == 0) ? H : pm;
+    sm[(slot - H) * T + pt] = hi[m];
   }
   __syncthreads();
 #pragma unroll
-  for (int m = 8; m < 16; m++) x[m] = sm[(m - 8) * T + t];
+  for (int m = H; m < E; m++) x[m] = sm[(m - H) * T + t];
   __syncthreads();  // staging is the engine's work buffer from here on
-  // first pass: value index m of (idx, slot): idx = (t + q*T) + r*(N/R0), slot = q*R0 + r  ->  m = q + r*(16/R0)
-  auto load = [&](int, int slot) { return x[(slot / R0) + (slot % R0) * (16 / R0)]; };
+  // first pass: value index m of (idx, slot): idx = (t + q*T) + r*(N/R0), slot = q*R0 + r  ->  m = q + r*(E/R0)
+  auto load = [&](int, int slot) { return x[(slot / R0) + (slot % R0) * (E / R0)]; };
   auto store = [&](int idx, float2 v, int) {
     if (active) __stcs(dst + idx, v);
   };
