@@ -742,7 +742,7 @@ struct b2f_pconv {
   int wp = 0, wp2 = 0;  // ring positions, cl_conv.cpp:144
   float2 *d_fdl = nullptr, *d_irs = nullptr, *d_tw = nullptr, *d_w2 = nullptr;
   float *d_tail = nullptr, *d_in1 = nullptr, *d_in2 = nullptr, *d_out = nullptr, *d_ir = nullptr;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second half of the channels in the pipelined host call
   Staging sg_in, sg_in2, sg_out;
   int cluster = 1;
   // general path (pts > 2^kPconvMaxLogP): batched real-FFT plans + pad / MAC / overlap-add kernels
@@ -762,6 +762,7 @@ struct b2f_pconv {
         delete p;
       }
     if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
     sg_in.release();
     sg_in2.release();
     sg_out.release();
@@ -1014,6 +1015,16 @@ static int pconv_enqueue(b2f_pconv *h, bool tv, float *d_out, const float *d_in1
   if (tv) h->wp2 = h->wp2 == 0 ? h->nparts - 1 : h->wp2 - 1;  // cl_conv.cpp:519
   return B2F_OK;
 }
+// fused path, static IR: one step for channels [c0, c0 + n) only (ring positions are NOT advanced here)
+static int pconv_launch_range(b2f_pconv *h, float *d_out, const float *d_in, int c0, int n, cudaStream_t st) {
+  const size_t ring = (size_t)c0 * h->nparts * h->pts, blk = (size_t)c0 * h->pts;
+  PconvArgs a;
+  a.fdl = h->d_fdl + ring, a.irs = h->d_irs + ring, a.tail = h->d_tail + blk;
+  a.in1 = d_in + blk, a.in2 = nullptr, a.out = d_out + blk;
+  a.tw = h->d_tw, a.w2 = h->d_w2;
+  a.nparts = h->nparts, a.wp = h->wp, a.wp2 = h->wp2;
+  return launch_pconv_step(h->logp, false, a, n, h->cluster, st);
+}
 extern "C" int b2f_pconv_process_dev(b2f_pconv *h, void *d_out, const void *d_in, void *stream) {
   if (!h || !d_out || !d_in || !al16(d_out) || !al16(d_in)) return B2F_ERR_INVALID_VALUE;
   B2F_ON_DEVICE(h->device);
@@ -1043,6 +1054,24 @@ extern "C" int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in)
     if ((rc = pconv_enqueue(h, false, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, nullptr, h->stream))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     memcpy(out, h->sg_out.pin, blk);
+    return B2F_OK;
+  }
+  // Many channels, blocks too large for the bounce buffer (the copies go straight from / to the caller's memory,
+  // asynchronously when it is pinned): the two halves of the channels run on two streams, so that the second
+  // half's upload overlaps the first half's kernel and the first half's download the second half's kernel.
+  if (!h->general() && h->channels >= 128 && blk > kBounceMax && !getenv("B2F_PCONV_NO_PIPELINE")) {
+    if (!h->stream2) CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    const int n0 = h->channels / 2, n1 = h->channels - n0;
+    const size_t b0 = (size_t)n0 * h->pts, bytes0 = b0 * sizeof(float), bytes1 = (size_t)n1 * h->pts * sizeof(float);
+    CK(cudaMemcpyAsync(h->d_in1, in, bytes0, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_in1 + b0, in + b0, bytes1, cudaMemcpyHostToDevice, h->stream2));
+    if ((rc = pconv_launch_range(h, h->d_out, h->d_in1, 0, n0, h->stream))) return rc;
+    if ((rc = pconv_launch_range(h, h->d_out, h->d_in1, n0, n1, h->stream2))) return rc;
+    CK(cudaMemcpyAsync(out, h->d_out, bytes0, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out + b0, h->d_out + b0, bytes1, cudaMemcpyDeviceToHost, h->stream2));
+    h->wp = h->wp != h->nparts - 1 ? h->wp + 1 : 0;  // cl_conv.cpp:424
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->stream2));
     return B2F_OK;
   }
   if ((rc = h2d(h->d_in1, in, blk, h->sg_in, h->stream))) return rc;

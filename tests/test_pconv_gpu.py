@@ -267,3 +267,32 @@ def test_both_mac_feeds(eng, port, monkeypatch, tma, pts, channels):
         assert rel_l2(y[:, k], np.stack([o.convolution(x[t, k]) for t in range(nb)])) < TOL
         o = port.pconv(cvs, pts)
         assert rel_l2(ytv[:, k], np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])) < TOL
+
+
+def test_pipelined_host_call_equals_device_path(eng, monkeypatch):
+    """Many channels with a block above 1 MB: the synchronous host call runs the two halves of the channels on two
+    streams (upload of one half overlapping the kernel of the other). Same bits as the single-stream form and as
+    the device-pointer entry point, over enough blocks to wrap the delay line, odd channel count included."""
+    import torch
+
+    pts, nparts, channels, nb = 512, 5, 1027, 8
+    rng = np.random.default_rng(11)
+    ir = (rng.standard_normal((channels, pts * nparts)) * 0.05).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, channels, pts)).astype(np.float32)
+
+    def host_run():
+        c = eng.Clpconv(0, pts * nparts, pts, channels=channels)
+        assert c.push_ir(ir.reshape(-1)) == 0
+        return run_stream(c, x)
+
+    y_pipe = host_run()
+    monkeypatch.setenv("B2F_PCONV_NO_PIPELINE", "1")
+    y_single = host_run()
+    assert np.array_equal(y_pipe, y_single)
+    c = eng.Clpconv(0, pts * nparts, pts, channels=channels)
+    assert c.push_ir(ir.reshape(-1)) == 0
+    d_y = torch.empty(channels, pts, device="cuda")
+    for t in range(nb):
+        assert c.convolution_dev(d_y, torch.from_numpy(x[t]).cuda()) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(d_y.cpu().numpy(), y_pipe[t])
