@@ -21,6 +21,7 @@
 #include "fft_cluster.cuh"
 #include "fft_kernels.cuh"
 #include "fft_large.cuh"
+#include "fft_sm.cuh"
 #include "pconv_kernels.cuh"
 
 using namespace b2f;
@@ -313,6 +314,48 @@ struct ClusterPlan {
   }
 };
 
+// ---- one-SM plan (fft_sm.cuh): N = 2^15 in one pass over HBM, one persistent CTA per SM ------------------------------
+struct SmPlan {
+  int grid = 0;
+  float2 *d_twb = nullptr, *d_twa = nullptr;
+  bool ok() const { return d_twb != nullptr; }
+  // B2F_FFT_SM=0 (read when the plan is created) selects the four-step launch pair of fft_large.cuh instead
+  static bool wanted(int logn) {
+    if (logn != SmGeom::LOGN) return false;
+    const char *e = getenv("B2F_FFT_SM");
+    return !(e && atoi(e) == 0);
+  }
+  int init(int device) {
+    const int N = SmGeom::N;
+    std::vector<float2> twb(5 * 1024), twa(5 * 32);
+    for (int b = 0; b < 5; b++) {
+      for (int c = 0; c < 1024; c++) twb[b * 1024 + c] = ref_twiddle((long long)c << b, N);  // W_N^(c 2^b)
+      for (int j = 0; j < 32; j++) twa[b * 32 + j] = ref_twiddle((long long)(32 * j) << b, N);  // W_1024^(j 2^b)
+    }
+    int rc;
+    if ((rc = upload(twb, &d_twb)) || (rc = upload(twa, &d_twa))) return rc;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    grid = nsm > 0 ? nsm : 1;
+    return B2F_OK;
+  }
+  void destroy() {
+    for (void *p : {(void *)d_twb, (void *)d_twa})
+      if (p) cudaFree(p);
+    d_twb = d_twa = nullptr;
+  }
+  template <bool INV, bool REAL>
+  int run(const float2 *in, float2 *out, const float2 *hw, int batch, float scale, cudaStream_t st) {
+    auto kern = fft_sm_kernel<INV, REAL>;
+    int rc = set_smem(kern, SmGeom::SMEM);
+    if (rc) return rc;
+    const int g = batch < grid ? batch : grid;
+    kern<<<g, SmGeom::THREADS, SmGeom::SMEM, st>>>(in, out, d_twb, d_twa, hw, batch, scale);
+    CK(cudaGetLastError());
+    return B2F_OK;
+  }
+};
+
 // ---- four-step plan for N > 2^kMaxSmemLogN ----------------------------------------------------------------
 struct LargePlan {
   int logn = 0, log1 = 0, log2 = 0, chunk = 1;
@@ -342,7 +385,10 @@ struct LargePlan {
     chunk = (int)(scratch_bytes / ((size_t)N * sizeof(float2)));
     if (chunk < 1) chunk = 1;
     if (chunk > max_batch) chunk = max_batch < 1 ? 1 : max_batch;
-    if (!fused_wanted()) CK(cudaMalloc((void **)&d_scratch, (size_t)chunk * N * sizeof(float2)));
+    return B2F_OK;  // the scratch matrix is allocated by the first launch pair that needs it (ensure_scratch)
+  }
+  int ensure_scratch() {
+    if (!d_scratch) CK(cudaMalloc((void **)&d_scratch, (size_t)chunk * ((size_t)1 << logn) * sizeof(float2)));
     return B2F_OK;
   }
   void destroy() {
@@ -357,6 +403,7 @@ struct LargePlan {
     using R = RowsGeom<L1, L2, RBT>;
     static_assert(!UNSPLIT || (INV && !REAL), "the fused unsplit precedes an inverse complex transform");
     int rc;
+    if ((rc = ensure_scratch())) return rc;
     if ((rc = set_smem(large_cols_kernel<L1, L2, INV>, L::SMEM_A))) return rc;
     if (UNSPLIT && (rc = set_smem(large_cols_unsplit_kernel<L1, L2>, L::SMEM_A))) return rc;
     if ((rc = set_smem(large_rows_kernel<L1, L2, INV, REAL, RBT>, R::SMEM))) return rc;
@@ -551,6 +598,7 @@ struct FftPlanCore {
   float2 *d_buf = nullptr;  // device buffer backing the host entry points
   LargePlan large;          // N > 2^kMaxSmemLogN
   ClusterPlan cluster;      // N = 2^13..2^15 on thread-block clusters (when selected)
+  SmPlan sm;                // N = 2^15: one pass over HBM, one transform per SM (fft_sm.cuh)
   cudaStream_t stream = nullptr;
   Staging sg_in, sg_out;
   bool is_large() const { return logn > kMaxSmemLogN; }
@@ -570,6 +618,10 @@ struct FftPlanCore {
     }
     if (ClusterPlan::wanted(logn)) {
       rc = cluster.init(logn);
+      if (rc) return rc;
+    }
+    if (SmPlan::wanted(logn)) {
+      rc = sm.init(dev);
       if (rc) return rc;
     }
     if (real) {
@@ -599,6 +651,7 @@ struct FftPlanCore {
     if (d_buf) cudaFree(d_buf);
     large.destroy();
     cluster.destroy();
+    sm.destroy();
     if (stream) cudaStreamDestroy(stream);
     sg_in.release();
     sg_out.release();
@@ -608,11 +661,15 @@ struct FftPlanCore {
     if (cluster.ok())
       return fwd ? cluster.run<false, false>(in, out, nullptr, batch, scale, st)
                  : cluster.run<true, false>(in, out, nullptr, batch, scale, st);
+    if (sm.ok())
+      return fwd ? sm.run<false, false>(in, out, nullptr, batch, scale, st)
+                 : sm.run<true, false>(in, out, nullptr, batch, scale, st);
     if (is_large()) return large.run_c2c(!fwd, in, out, batch, scale, st);
     return launch_cfft(logn, !fwd, in, out, d_tw, batch, scale, st);
   }
   int run_real(const float2 *in, float2 *out, int batch, cudaStream_t st) {
     if (cluster.ok() && fwd) return cluster.run<false, true>(in, out, d_w2, batch, fwd_scale(), st);
+    if (sm.ok() && fwd) return sm.run<false, true>(in, out, d_hw, batch, fwd_scale(), st);
     if (is_large()) return large.run_real(!fwd, in, out, d_w2, d_hw, batch, fwd_scale(), st);
     return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, d_hw, batch, fwd_scale(), st);
   }

@@ -1,0 +1,403 @@
+// fft_sm.cuh -- "one SM, one transform": the 32768-point complex FFT (= the 65536-point real FFT of BASELINE
+// config 5a) in ONE pass over HBM, every transform carried start to finish by one persistent 512-thread CTA.
+//
+// What it replaces in the reference: the reorder launch + 15 radix-2 stage launches of Clcfft::fft()
+// (cl_fft.cpp:138-151) and, for the real transform, the `conv` split launch behind them (cl_fft.cpp:178-191,
+// 267-282), each of which re-reads and re-writes the whole array in global memory. Round 1 ran this length as a
+// four-step pair of launches with a scratch matrix through HBM (fft_large.cuh: 2 x the algorithmic traffic).
+//
+// Factorisation N = 32 x 32 x 32, input index n = 1024 j1 + 32 j2 + j3, output index k = k1 + 32 k2 + 1024 k3:
+//   P1      thread = column c = 32 j2 + j3 (two columns per thread): 32 loads at stride 1024 (a warp reads 256
+//           contiguous bytes per j1), radix-32 over j1 -> k1, times W_N^(c k1).
+//   pass A  warp = row k1, lane = j3: radix-32 over j2 -> k2, times W_1024^(j3 k2); the row is private to the
+//           warp, so the pass needs no CTA barrier.
+//   pass B  thread = (row k1, k2), a warp holds 16 rows x the two values {a, 31-a} of k2: radix-32 over j3 -> k3,
+//           stores X[k1 + 32 k2 + 1024 k3] in 128-byte lines. Real transform: the split of cl_fft.cpp:178-191 is
+//           fused here, see the comment at the kernel.
+//
+// A transform is 256 KiB; an SM has 227 KB of shared memory. So the rows are processed as two JOBS of 16 rows
+// (139 KB of padded shared memory): P1 computes all 32 outputs of a column, stores the first job's 16 straight into
+// the row buffers and parks the second job's 16 in TENSOR MEMORY (tcgen05.st, thread-private columns: 512 threads
+// x 64 columns x 4 B = 128 KiB of the SM's 256 KiB TMEM), from where they are moved into the row buffers
+// (tcgen05.ld) once the first job has left them. TMEM is used as what it physically is -- a second on-chip
+// scratch-pad next to shared memory -- not for MMA. (A variant parking the same values in an L2-resident global
+// scratch measured 2.34 vs 2.79 TB/s in the first version of this kernel and was dropped.)
+// The next transform of the CTA is requested into L2 with cp.async.bulk.prefetch (TMA engine, no registers, no
+// shared memory) while the current one is being computed, so P1's loads are L2 hits.
+//
+// HBM traffic: the algorithmic bytes, once. Shared-memory traffic per point: P1 store, A load/store, B load (+ TMEM
+// round trip for half the points). Barriers: six per transform.
+#pragma once
+
+#include "fft_core.cuh"
+
+namespace b2f {
+
+// ---- radix-32 butterfly: natural order in, natural order out ------------------------------------------------------
+template <bool INV>
+__device__ __forceinline__ void dft32(float2 (&v)[32]) {
+  constexpr float kC[16] = {1.f,
+                            0.98078528040323043f,
+                            0.92387953251128674f,
+                            0.83146961230254524f,
+                            0.70710678118654757f,
+                            0.55557023301960229f,
+                            0.38268343236508984f,
+                            0.19509032201612833f,
+                            0.f,
+                            -0.19509032201612833f,
+                            -0.38268343236508984f,
+                            -0.55557023301960229f,
+                            -0.70710678118654757f,
+                            -0.83146961230254524f,
+                            -0.92387953251128674f,
+                            -0.98078528040323043f};
+  constexpr float kS[16] = {0.f,
+                            0.19509032201612825f,
+                            0.38268343236508978f,
+                            0.55557023301960218f,
+                            0.70710678118654757f,
+                            0.83146961230254524f,
+                            0.92387953251128674f,
+                            0.98078528040323043f,
+                            1.f,
+                            0.98078528040323043f,
+                            0.92387953251128674f,
+                            0.83146961230254524f,
+                            0.70710678118654757f,
+                            0.55557023301960218f,
+                            0.38268343236508978f,
+                            0.19509032201612825f};
+  float2 e[16], o[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    e[i] = v[2 * i];
+    o[i] = v[2 * i + 1];
+  }
+  dft16<INV>(e);
+  dft16<INV>(o);
+#pragma unroll
+  for (int i = 1; i < 16; i++) o[i] = (i == 8) ? cquarter<INV>(o[i]) : cmulc<INV>(o[i], kC[i], kS[i]);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    v[i] = cadd(e[i], o[i]);
+    v[i + 16] = csub(e[i], o[i]);
+  }
+}
+
+// v[m] *= W^m for m = 1..31, given W^1, W^2, W^4, W^8, W^16 (base[b] = W^(2^b)): the other 26 powers are products
+// built depth-first over the bits of m, so at most four partial products are alive at a time (26 complex
+// multiplications, at most four roundings deep, ~3e-7) -- the full table of a pass would be 31 loads per
+// butterfly through the LSU data pipe, which is the SM-side limit of the FFT kernels (fft_core.cuh).
+template <int BIT, int M, bool HAVE>
+__device__ __forceinline__ void tw_tree(float2 (&v)[32], float2 p, const float2 (&base)[5]) {
+  if constexpr (BIT < 0) {
+    if constexpr (HAVE) v[M] = cmul(v[M], p);
+  } else {
+    tw_tree<BIT - 1, M, HAVE>(v, p, base);
+    float2 q = base[BIT];
+    if constexpr (HAVE) q = cmul(p, q);
+    tw_tree<BIT - 1, (M | (1 << BIT)), true>(v, q, base);
+  }
+}
+
+// ---- tensor memory as a scratch-pad -----------------------------------------------------------------------------
+// 32x32b shape: lane i of the issuing warp reads / writes 32-bit columns [col, col + n) of TMEM lane 32 (warp % 4) + i,
+// i.e. storage private to the thread. Address = (lane << 16) | column.
+namespace tmem {
+__device__ __forceinline__ void alloc(uint32_t smem_dst, uint32_t cols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dealloc(uint32_t taddr, uint32_t cols) {  // the allocating warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// eight complex values <-> sixteen columns
+__device__ __forceinline__ void st8(uint32_t taddr, const float2 (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
+          "r"(taddr),
+      "r"(__float_as_uint(v[0].x)), "r"(__float_as_uint(v[0].y)), "r"(__float_as_uint(v[1].x)), "r"(__float_as_uint(v[1].y)),
+      "r"(__float_as_uint(v[2].x)), "r"(__float_as_uint(v[2].y)), "r"(__float_as_uint(v[3].x)), "r"(__float_as_uint(v[3].y)),
+      "r"(__float_as_uint(v[4].x)), "r"(__float_as_uint(v[4].y)), "r"(__float_as_uint(v[5].x)), "r"(__float_as_uint(v[5].y)),
+      "r"(__float_as_uint(v[6].x)), "r"(__float_as_uint(v[6].y)), "r"(__float_as_uint(v[7].x)), "r"(__float_as_uint(v[7].y))
+      : "memory");
+}
+__device__ __forceinline__ void ld8(uint32_t taddr, float2 (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+        "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
+      : "r"(taddr)
+      : "memory");
+}
+// the values of ld8 may be used after this; passing them through the asm keeps the compiler from moving uses up
+__device__ __forceinline__ void wait_ld8(float2 (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[2].x), "+f"(v[2].y), "+f"(v[3].x),
+                 "+f"(v[3].y), "+f"(v[4].x), "+f"(v[4].y), "+f"(v[5].x), "+f"(v[5].y), "+f"(v[6].x), "+f"(v[6].y),
+                 "+f"(v[7].x), "+f"(v[7].y)::"memory");
+}
+}  // namespace tmem
+
+// ---- geometry ---------------------------------------------------------------------------------------------------------
+struct SmGeom {
+  static constexpr int LOGN = 15, N = 1 << LOGN;
+  static constexpr int THREADS = 512;
+  // exchange layout of a row (written by pass A, read by pass B): [k2][j3] float2, 16 bytes of padding per k2 line
+  // and 16 per row: pass B's 128-bit reads (8 lanes = 8 rows, or 8 rows of the other k2) and pass A's 64-bit writes
+  // (32 consecutive j3) are both bank-conflict free. P1 writes the row as [j2][j3] into the first 8 KiB.
+  static constexpr int K2S = 32 * 8 + 16;
+  static constexpr int ROW = 32 * K2S + 16;
+  static constexpr int OFF_Z = 16 * ROW;              // row k1 = 0 of the real transform, [k2 + 32 k3] float2
+  static constexpr int OFF_TWB = OFF_Z + 1024 * 8;    // P1 twiddle bases [5][1024]: W_N^(c 2^b)
+  static constexpr int OFF_TWA = OFF_TWB + 5 * 1024 * 8;  // pass-A twiddle bases [5][32]: W_1024^(j3 2^b)
+  static constexpr int OFF_HW = OFF_TWA + 5 * 32 * 8;     // folded split table, entries 0..1023
+  static constexpr int OFF_HW32 = OFF_HW + 1024 * 8;      // folded split table, entries 32 m (row k1 = 0)
+  static constexpr int OFF_MISC = OFF_HW32 + 512 * 8;
+  static constexpr int SMEM = OFF_MISC + 16;
+  // tensor memory, per thread (4 warps share a lane quarter): columns [0, 64) hold the second job's P1 outputs of the
+  // thread's two columns; real transform: columns [64, 128) park the first job's pass-B results
+  static constexpr int TCOLS_THREAD_C = 64, TCOLS_THREAD_R = 128;
+};
+
+// exp(-i pi k / 32), k = 0..31: (kSplitC[k], -kSplitS[k])
+__device__ constexpr float kSplitC[32] = {
+    1.f,
+    0.99518472667219693f,  0.98078528040323043f,  0.95694033573220882f,  0.92387953251128674f,  0.88192126434835505f,
+    0.83146961230254524f,  0.77301045336273699f,  0.70710678118654757f,  0.63439328416364549f,  0.55557023301960229f,
+    0.47139673682599770f,  0.38268343236508984f,  0.29028467725446233f,  0.19509032201612833f,  0.09801714032956077f,
+    0.f,
+    -0.09801714032956077f, -0.19509032201612833f, -0.29028467725446233f, -0.38268343236508984f, -0.47139673682599770f,
+    -0.55557023301960229f, -0.63439328416364549f, -0.70710678118654757f, -0.77301045336273699f, -0.83146961230254524f,
+    -0.88192126434835505f, -0.92387953251128674f, -0.95694033573220882f, -0.98078528040323043f, -0.99518472667219693f};
+__device__ constexpr float kSplitS[32] = {
+    0.f,
+    0.09801714032956060f, 0.19509032201612825f, 0.29028467725446233f, 0.38268343236508978f, 0.47139673682599764f,
+    0.55557023301960218f, 0.63439328416364549f, 0.70710678118654757f, 0.77301045336273699f, 0.83146961230254524f,
+    0.88192126434835505f, 0.92387953251128674f, 0.95694033573220882f, 0.98078528040323043f, 0.99518472667219693f,
+    1.f,
+    0.99518472667219693f, 0.98078528040323043f, 0.95694033573220882f, 0.92387953251128674f, 0.88192126434835505f,
+    0.83146961230254524f, 0.77301045336273699f, 0.70710678118654757f, 0.63439328416364549f, 0.55557023301960218f,
+    0.47139673682599764f, 0.38268343236508978f, 0.29028467725446233f, 0.19509032201612825f, 0.09801714032956060f};
+
+// Job `job` holds rows k1 = 16 job + s, s = 0..15: pass B stores 128-byte lines.
+//
+// Real transform (the split of cl_fft.cpp:178-191 fused into pass B). The partner of element (k1, k2, k3) is
+// (32 - k1, 31 - k2, 31 - k3): a row of the OTHER job, but the same warp (which holds k2 = a and 31 - a), the lane
+// (16 - s, other k2) and the register 31 - k3. So job 0 stores nothing to global memory: its pass B parks the
+// thread's 32 results in tensor memory; job 1 fetches them back eight at a time, shuffles them to the partner lane,
+// evaluates every pair once and stores BOTH members -- its own (rows 16..31) and the partner's (rows 15..1) -- as
+// full 128-byte lines. Row 16 is its own mirror (partner lane in the same job); row 0 is too, but with the irregular
+// pattern (k2, k3) <-> (32 - k2, 31 - k3) and the two special elements (packed DC/Nyquist, untouched bin N/2:
+// SURVEY Q2/Q3), so it is split in an 8 KiB shared-memory buffer Z and stored by the row-16 lanes, whose partner
+// slot is free, completing the partner's lines.
+template <bool INV, bool REAL>
+__global__ void __launch_bounds__(SmGeom::THREADS, 1)
+    fft_sm_kernel(const float2 *in, float2 *out, const float2 *__restrict__ twb_g, const float2 *__restrict__ twa_g,
+                  const float2 *__restrict__ hw, int batch, float scale) {
+  using G = SmGeom;
+  static_assert(!(REAL && INV), "the inverse real transform (unsplit first) is not built on this kernel");
+  constexpr int N = G::N;
+  constexpr int TCOLS = REAL ? G::TCOLS_THREAD_R : G::TCOLS_THREAD_C;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  unsigned char *rows = smraw;
+  float2 *Z = reinterpret_cast<float2 *>(smraw + G::OFF_Z);
+  float2 *twb = reinterpret_cast<float2 *>(smraw + G::OFF_TWB);
+  float2 *twa = reinterpret_cast<float2 *>(smraw + G::OFF_TWA);
+  float2 *hwb = reinterpret_cast<float2 *>(smraw + G::OFF_HW);
+  float2 *hw32 = reinterpret_cast<float2 *>(smraw + G::OFF_HW32);
+  uint32_t *misc = reinterpret_cast<uint32_t *>(smraw + G::OFF_MISC);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < 5 * 1024; i += G::THREADS) twb[i] = __ldg(&twb_g[i]);
+  if (tid < 5 * 32) twa[tid] = __ldg(&twa_g[tid]);
+  if constexpr (REAL) {
+    for (int i = tid; i < 1024; i += G::THREADS) hwb[i] = __ldg(&hw[i]);
+    hw32[tid] = __ldg(&hw[32 * tid]);
+  }
+  if (warp == 0) tmem::alloc((uint32_t)__cvta_generic_to_shared(misc), 4 * TCOLS);
+  tmem::fence_before();
+  __syncthreads();
+  tmem::fence_after();
+  // this thread's private columns: TMEM lane 32 (warp % 4) + lane, columns TCOLS (warp / 4) ...
+  const uint32_t taddr = misc[0] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TCOLS);
+  const float hs = 0.5f * scale;
+
+  for (int t = blockIdx.x; t < batch; t += gridDim.x) {
+    const float2 *src = in + (size_t)t * N;
+    float2 *dst = out + (size_t)t * N;
+
+    // ---- P1: radix-32 over j1 for columns c = tid, tid + 512 ------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int c = tid + 512 * r;
+      float2 v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] = __ldcs(&src[1024 * j + c]);
+      float2 base[5];
+#pragma unroll
+      for (int b = 0; b < 5; b++) {
+        base[b] = twb[b * 1024 + c];
+        if (INV) base[b].y = -base[b].y;
+      }
+      dft32<INV>(v);
+      tw_tree<4, 0, false>(v, make_float2(1.f, 0.f), base);
+#pragma unroll
+      for (int s = 0; s < 16; s++) *reinterpret_cast<float2 *>(rows + s * G::ROW + c * 8) = v[s];
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        float2 h8[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) h8[i] = v[16 + 8 * g + i];
+        tmem::st8(taddr + 32 * r + 16 * g, h8);
+      }
+    }
+    tmem::wait_st();
+    __syncthreads();
+
+#pragma unroll 1
+    for (int job = 0; job < 2; job++) {
+      if (job == 1) {
+        // the CTA's next transform -> L2 (eight 32 KiB bulk prefetches by the TMA engine), half a transform ahead:
+        // early enough to cover the HBM latency, late enough not to crowd the L2 (148 CTAs x 256 KiB)
+        if (tid < 8 && t + (int)gridDim.x < batch) {
+          const float2 *nx = in + (size_t)(t + gridDim.x) * N + tid * 4096;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"(32768) : "memory");
+        }
+        // the second job's rows: tensor memory -> row buffers
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const int c = tid + 512 * r;
+          float2 ha[8], hb[8];
+          tmem::ld8(taddr + 32 * r, ha);
+          tmem::ld8(taddr + 32 * r + 16, hb);
+          tmem::wait_ld8(ha);
+          tmem::wait_ld8(hb);
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            *reinterpret_cast<float2 *>(rows + i * G::ROW + c * 8) = ha[i];
+            *reinterpret_cast<float2 *>(rows + (8 + i) * G::ROW + c * 8) = hb[i];
+          }
+        }
+        __syncthreads();
+      }
+
+      // ---- pass A: warp = row slot, lane = j3, registers = j2 ---------------------------------------------------
+      {
+        unsigned char *row = rows + warp * G::ROW;
+        float2 v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = *reinterpret_cast<const float2 *>(row + (j * 32 + lane) * 8);
+        float2 base[5];
+#pragma unroll
+        for (int b = 0; b < 5; b++) {
+          base[b] = twa[b * 32 + lane];
+          if (INV) base[b].y = -base[b].y;
+        }
+        __syncwarp();  // the whole row is in registers before its buffer is overwritten in the exchange layout
+        dft32<INV>(v);
+        tw_tree<4, 0, false>(v, make_float2(1.f, 0.f), base);
+#pragma unroll
+        for (int k = 0; k < 32; k++) *reinterpret_cast<float2 *>(row + k * G::K2S + lane * 8) = v[k];
+      }
+      __syncthreads();
+
+      // ---- pass B: thread = (row slot s, k2), registers = j3 -> k3 --------------------------------------------
+      {
+        const int s = lane & 15, h = lane >> 4;
+        const int k2 = h ? 31 - warp : warp;
+        const int k1 = 16 * job + s;
+        const unsigned char *p = rows + s * G::ROW + k2 * G::K2S;
+        float2 v[32];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          const float4 f = *reinterpret_cast<const float4 *>(p + 16 * q);
+          v[2 * q] = make_float2(f.x, f.y);
+          v[2 * q + 1] = make_float2(f.z, f.w);
+        }
+        dft32<INV>(v);
+        float2 *o = dst + k1 + 32 * k2;
+        if constexpr (!REAL) {
+#pragma unroll
+          for (int k3 = 0; k3 < 32; k3++) o[1024 * k3] = cscale(v[k3], scale);
+        } else if (job == 0) {
+          if (s == 0) {
+#pragma unroll
+            for (int k3 = 0; k3 < 32; k3++) Z[k2 + 32 * k3] = v[k3];
+          }
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            float2 h8[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) h8[i] = v[8 * g + i];
+            tmem::st8(taddr + 64 + 16 * g, h8);
+          }
+          tmem::wait_st();
+        } else {
+          // k = k1 + 32 k2 + 1024 k3 (own, rows 16..31), N - k = (16 - s) + 32 (31 - k2) + 1024 (31 - k3) (partner).
+          // hw(k) = hw(k1 + 32 k2) exp(-i pi k3 / 32), extended analytically past N/2, where hw(N - k) = conj(hw(k)).
+          const float2 hbase = hwb[k1 + 32 * k2];
+          const bool s0 = (s == 0);
+          const int srclane = (s0 ? 0 : 16 - s) + 16 * (1 - h);
+          // partner slot of the row-16 lanes: row 0, element (31 - k2, 31 - k3), already split in Z
+          float2 *om = dst + (N - (k1 + 32 * k2)) - (s0 ? 16 : 0);
+          const float2 *zp = Z + (31 - k2) + 32 * 31;
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            float2 pk[8];  // pk[i] = this thread's job-0 result 24 - 8 g + i
+            tmem::ld8(taddr + 64 + 2 * (24 - 8 * g), pk);
+            tmem::wait_ld8(pk);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int k3 = 8 * g + j;
+              const float2 snd = s0 ? v[31 - k3] : pk[7 - j];
+              float2 rcv;
+              rcv.x = __shfl_sync(0xffffffffu, snd.x, srclane);
+              rcv.y = __shfl_sync(0xffffffffu, snd.y, srclane);
+              float2 hk = k3 ? cmulc<false>(hbase, kSplitC[k3], kSplitS[k3]) : hbase;
+              float2 mine = v[k3], other = rcv;
+              if (k3 < 16) {
+                rfft_pair_folded<false>(mine, other, hk, hs);
+              } else {
+                rfft_pair_folded<false>(other, mine, cconj(hk), hs);
+              }
+              if (s0) other = zp[-32 * k3];
+              o[1024 * k3] = mine;
+              om[-1024 * k3] = other;
+            }
+          }
+        }
+      }
+      __syncthreads();  // the row buffers are free again (and Z is complete)
+
+      if constexpr (REAL) {
+        if (job == 0) {
+          // row k1 = 0: X[32 m], m = k2 + 32 k3, pairs (m, 1024 - m), split in place; m = 0 is the packed (DC, Nyquist)
+          // element and m = 512 is bin N/2, which the reference's split never visits (cl_fft.cpp:278).
+          // Read again in job 1's pass B, several barriers from here.
+          const int m = tid;
+          if (m == 0) {
+            const float2 z0 = Z[0];
+            Z[0] = make_float2((z0.x + z0.y) * hs, (z0.x - z0.y) * hs);
+            Z[512] = cscale(Z[512], scale);
+          } else {
+            float2 a = Z[m], b = Z[1024 - m];
+            rfft_pair_folded<false>(a, b, hw32[m], hs);
+            Z[m] = a;
+            Z[1024 - m] = b;
+          }
+        }
+      }
+    }
+  }
+  tmem::fence_before();
+  __syncthreads();
+  if (warp == 0) tmem::dealloc(misc[0], 4 * TCOLS);
+}
+
+}  // namespace b2f
