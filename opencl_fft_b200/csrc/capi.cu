@@ -327,13 +327,14 @@ struct SmPlan {
   }
   int init(int device) {
     const int N = SmGeom::N;
-    std::vector<float2> twb(5 * 1024), twa(5 * 32);
-    for (int b = 0; b < 5; b++) {
-      for (int c = 0; c < 1024; c++) twb[b * 1024 + c] = ref_twiddle((long long)c << b, N);  // W_N^(c 2^b)
-      for (int j = 0; j < 32; j++) twa[b * 32 + j] = ref_twiddle((long long)(32 * j) << b, N);  // W_1024^(j 2^b)
-    }
+    std::vector<float2> twn(5 * 32), twa(5 * 32);
+    for (int b = 0; b < 5; b++)
+      for (int j = 0; j < 32; j++) {
+        twn[b * 32 + j] = ref_twiddle((long long)j << b, N);         // W_N^(j 2^b)
+        twa[b * 32 + j] = ref_twiddle((long long)(32 * j) << b, N);  // W_1024^(j 2^b)
+      }
     int rc;
-    if ((rc = upload(twb, &d_twb)) || (rc = upload(twa, &d_twa))) return rc;
+    if ((rc = upload(twn, &d_twb)) || (rc = upload(twa, &d_twa))) return rc;
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
     grid = nsm > 0 ? nsm : 1;

@@ -30,6 +30,7 @@
 #pragma once
 
 #include "fft_core.cuh"
+#include "tma_utils.cuh"
 
 namespace b2f {
 
@@ -153,13 +154,14 @@ struct SmGeom {
   // (32 consecutive j3) are both bank-conflict free. P1 writes the row as [j2][j3] into the first 8 KiB.
   static constexpr int K2S = 32 * 8 + 16;
   static constexpr int ROW = 32 * K2S + 16;
-  static constexpr int OFF_Z = 16 * ROW;              // row k1 = 0 of the real transform, [k2 + 32 k3] float2
-  static constexpr int OFF_TWB = OFF_Z + 1024 * 8;    // P1 twiddle bases [5][1024]: W_N^(c 2^b)
-  static constexpr int OFF_TWA = OFF_TWB + 5 * 1024 * 8;  // pass-A twiddle bases [5][32]: W_1024^(j3 2^b)
-  static constexpr int OFF_HW = OFF_TWA + 5 * 32 * 8;     // folded split table, entries 0..1023
-  static constexpr int OFF_HW32 = OFF_HW + 1024 * 8;      // folded split table, entries 32 m (row k1 = 0)
+  static constexpr int OFF_SP = 16 * ROW;             // staging of P1's round 1, runs j1 = 16..31 (64 KiB)
+  static constexpr int OFF_Z = OFF_SP + 16 * 4096;    // row k1 = 0 of the real transform, [k2][k3] float2
+  static constexpr int OFF_TWN = OFF_Z + 1024 * 8;    // P1 twiddle bases [5][32]: W_N^(j3 2^b)
+  static constexpr int OFF_TWA = OFF_TWN + 5 * 32 * 8;  // pass-A twiddle bases [5][32]: W_1024^(j 2^b) (also W_N^(32 j2 2^b))
+  static constexpr int OFF_HW = OFF_TWA + 5 * 32 * 8;   // folded split table, entries 0..1023
+  static constexpr int OFF_HW32 = OFF_HW + 1024 * 8;    // folded split table, entries 32 m (row k1 = 0)
   static constexpr int OFF_MISC = OFF_HW32 + 512 * 8;
-  static constexpr int SMEM = OFF_MISC + 16;
+  static constexpr int SMEM = OFF_MISC + 32;  // TMEM base address, three mbarriers
   // tensor memory, per thread (4 warps share a lane quarter): columns [0, 64) hold the second job's P1 outputs of the
   // thread's two columns; real transform: columns [64, 128) park the first job's pass-B results
   static constexpr int TCOLS_THREAD_C = 64, TCOLS_THREAD_R = 128;
@@ -198,7 +200,7 @@ __device__ constexpr float kSplitS[32] = {
 // slot is free, completing the partner's lines.
 template <bool INV, bool REAL>
 __global__ void __launch_bounds__(SmGeom::THREADS, 1)
-    fft_sm_kernel(const float2 *in, float2 *out, const float2 *__restrict__ twb_g, const float2 *__restrict__ twa_g,
+    fft_sm_kernel(const float2 *in, float2 *out, const float2 *__restrict__ twn_g, const float2 *__restrict__ twa_g,
                   const float2 *__restrict__ hw, int batch, float scale) {
   using G = SmGeom;
   static_assert(!(REAL && INV), "the inverse real transform (unsplit first) is not built on this kernel");
@@ -207,15 +209,18 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   extern __shared__ __align__(16) unsigned char smraw[];
   unsigned char *rows = smraw;
   float2 *Z = reinterpret_cast<float2 *>(smraw + G::OFF_Z);
-  float2 *twb = reinterpret_cast<float2 *>(smraw + G::OFF_TWB);
+  unsigned char *sp = smraw + G::OFF_SP;
+  float2 *twn = reinterpret_cast<float2 *>(smraw + G::OFF_TWN);
   float2 *twa = reinterpret_cast<float2 *>(smraw + G::OFF_TWA);
   float2 *hwb = reinterpret_cast<float2 *>(smraw + G::OFF_HW);
   float2 *hw32 = reinterpret_cast<float2 *>(smraw + G::OFF_HW32);
   uint32_t *misc = reinterpret_cast<uint32_t *>(smraw + G::OFF_MISC);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < 5 * 1024; i += G::THREADS) twb[i] = __ldg(&twb_g[i]);
-  if (tid < 5 * 32) twa[tid] = __ldg(&twa_g[tid]);
+  if (tid < 5 * 32) {
+    twn[tid] = __ldg(&twn_g[tid]);
+    twa[tid] = __ldg(&twa_g[tid]);
+  }
   if constexpr (REAL) {
     for (int i = tid; i < 1024; i += G::THREADS) hwb[i] = __ldg(&hw[i]);
     hw32[tid] = __ldg(&hw[32 * tid]);
@@ -227,22 +232,59 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   // this thread's private columns: TMEM lane 32 (warp % 4) + lane, columns TCOLS (warp / 4) ...
   const uint32_t taddr = misc[0] + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TCOLS);
   const float hs = 0.5f * scale;
+  // Both rounds of P1 are fed by the TMA engine (cp.async.bulk, SASS UBLKCP), 32 runs of 4 KiB each:
+  //   round 0 (columns 0..511 of the NEXT transform) lands in the row buffers as soon as the last pass B of the
+  //   current transform has read them (m_free: 16 warps arrived), so its HBM latency hides behind that pass's
+  //   butterflies and stores;
+  //   round 1 (columns 512..1023) is requested when round 0 is in registers and lands, while round 0 is being
+  //   computed, where round 0's results do not go: runs 0..15 in the second halves of the 16 rows, runs 16..31 in
+  //   a 64 KiB staging area.
+  const uint32_t m_free = tma::smem_u32(misc + 2), m_full0 = tma::smem_u32(misc + 4), m_full1 = tma::smem_u32(misc + 6);
+  auto stage_round = [&](int round, int tn) {  // the 32 lanes of one warp, one run each
+    const float2 *nx = in + (size_t)tn * N + 1024 * lane + 512 * round;
+    const uint32_t mb = round ? m_full1 : m_full0;
+    unsigned char *d = round == 0 ? rows + lane * 4096 : (lane < 16 ? rows + lane * G::ROW + 4096 : sp + (lane - 16) * 4096);
+    if (lane == 0) tma::mbar_expect_tx(mb, 32 * 4096);
+    __syncwarp();
+    tma::bulk_g2s(tma::smem_u32(d), nx, 4096, mb);
+  };
+  if (tid == 0) {
+    tma::mbar_init(m_free, 16);
+    tma::mbar_init(m_full0, 1);
+    tma::mbar_init(m_full1, 1);
+    tma::fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 0) stage_round(0, blockIdx.x);
+  uint32_t par = 0;
 
-  for (int t = blockIdx.x; t < batch; t += gridDim.x) {
-    const float2 *src = in + (size_t)t * N;
+  for (int t = blockIdx.x; t < batch; t += gridDim.x, par ^= 1) {
     float2 *dst = out + (size_t)t * N;
+    const bool more = t + (int)gridDim.x < batch;
 
     // ---- P1: radix-32 over j1 for columns c = tid, tid + 512 ------------------------------------------------------
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const int c = tid + 512 * r;
       float2 v[32];
+      if (r == 0) {
+        tma::mbar_wait(m_full0, par);
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] = __ldcs(&src[1024 * j + c]);
+        for (int j = 0; j < 32; j++) v[j] = *reinterpret_cast<const float2 *>(rows + j * 4096 + tid * 8);
+        __syncthreads();  // round 0 is in registers: the row buffers may be written, by round 1's runs too
+        if (warp == 0) stage_round(1, t);
+      } else {
+        tma::mbar_wait(m_full1, par);
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          v[j] = *reinterpret_cast<const float2 *>((j < 16 ? rows + j * G::ROW + 4096 : sp + (j - 16) * 4096) + tid * 8);
+        __syncthreads();  // round 1 is in registers: the second halves of the rows may be written
+      }
+      // W_N^(c 2^b), c = 32 j2 + j3 (j2 = warp + 16 r, j3 = lane), as the product of two table entries
       float2 base[5];
 #pragma unroll
       for (int b = 0; b < 5; b++) {
-        base[b] = twb[b * 1024 + c];
+        base[b] = cmul(twa[b * 32 + warp + 16 * r], twn[b * 32 + lane]);
         if (INV) base[b].y = -base[b].y;
       }
       dft32<INV>(v);
@@ -263,11 +305,12 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
 #pragma unroll 1
     for (int job = 0; job < 2; job++) {
       if (job == 1) {
-        // the CTA's next transform -> L2 (eight 32 KiB bulk prefetches by the TMA engine), half a transform ahead:
-        // early enough to cover the HBM latency, late enough not to crowd the L2 (148 CTAs x 256 KiB)
-        if (tid < 8 && t + (int)gridDim.x < batch) {
-          const float2 *nx = in + (size_t)(t + gridDim.x) * N + tid * 4096;
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"(32768) : "memory");
+        // columns 512..1023 of the CTA's next transform (P1's round 1 reads them with plain loads) -> L2, 32 bulk
+        // prefetches of 4 KiB by the TMA engine, half a transform ahead: early enough to cover the HBM latency, late
+        // enough not to crowd the L2
+        if (tid < 32 && more) {
+          const float2 *nx = in + (size_t)(t + gridDim.x) * N + 1024 * tid + 512;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"(4096) : "memory");
         }
         // the second job's rows: tensor memory -> row buffers
 #pragma unroll
@@ -307,12 +350,16 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
       }
       __syncthreads();
 
-      // ---- pass B: thread = (row slot s, k2), registers = j3 -> k3 --------------------------------------------
+      // ---- pass B: thread = (row slot, k2), registers = j3 -> k3 --------------------------------------------------
       {
         const int s = lane & 15, h = lane >> 4;
-        const int k2 = h ? 31 - warp : warp;
-        const int k1 = 16 * job + s;
-        const unsigned char *p = rows + s * G::ROW + k2 * G::K2S;
+        // Real transform, job 0: the lane takes the row and the k2 its job-1 self will need as partner, i.e. row
+        // (16 - s) mod 16 and the warp's OTHER k2 -- what it parks in tensor memory is then its own partner data.
+        const bool mirrored = REAL && job == 0;
+        const int slot = mirrored ? ((16 - s) & 15) : s;
+        const int k2 = (h != (int)mirrored) ? 31 - warp : warp;
+        const int k1 = 16 * job + slot;
+        const unsigned char *p = rows + slot * G::ROW + k2 * G::K2S;
         float2 v[32];
 #pragma unroll
         for (int q = 0; q < 16; q++) {
@@ -320,15 +367,25 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
           v[2 * q] = make_float2(f.x, f.y);
           v[2 * q + 1] = make_float2(f.z, f.w);
         }
+        if (job == 1) {
+          __syncwarp();
+          if (lane == 0) tma::mbar_arrive(m_free);
+          if (warp == 0 && more) {
+            tma::mbar_wait(m_free, par);
+            stage_round(0, t + gridDim.x);
+          }
+          __syncwarp();
+        }
         dft32<INV>(v);
         float2 *o = dst + k1 + 32 * k2;
         if constexpr (!REAL) {
 #pragma unroll
           for (int k3 = 0; k3 < 32; k3++) o[1024 * k3] = cscale(v[k3], scale);
         } else if (job == 0) {
-          if (s == 0) {
+          if (s == 0) {  // row 0 -> Z[k2][k3]
 #pragma unroll
-            for (int k3 = 0; k3 < 32; k3++) Z[k2 + 32 * k3] = v[k3];
+            for (int q = 0; q < 16; q++)
+              *reinterpret_cast<float4 *>(Z + 32 * k2 + 2 * q) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
           }
 #pragma unroll
           for (int g = 0; g < 4; g++) {
@@ -343,53 +400,66 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
           // hw(k) = hw(k1 + 32 k2) exp(-i pi k3 / 32), extended analytically past N/2, where hw(N - k) = conj(hw(k)).
           const float2 hbase = hwb[k1 + 32 * k2];
           const bool s0 = (s == 0);
-          const int srclane = (s0 ? 0 : 16 - s) + 16 * (1 - h);
-          // partner slot of the row-16 lanes: row 0, element (31 - k2, 31 - k3), already split in Z
+          // Row 16 (s = 0) is its own mirror: the partner is the warp's other row-16 lane. The two swap their results
+          // through Z16 (8 KiB of the round-1 staging area, idle now). Their partner slot in the stores is free and
+          // takes row 0, element (31 - k2, 31 - k3), already split in Z.
+          float2 *z16 = reinterpret_cast<float2 *>(sp);
+          if (s0) {
+#pragma unroll
+            for (int q = 0; q < 16; q++)
+              *reinterpret_cast<float4 *>(z16 + 32 * k2 + 2 * q) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+          }
+          __syncwarp();
           float2 *om = dst + (N - (k1 + 32 * k2)) - (s0 ? 16 : 0);
-          const float2 *zp = Z + (31 - k2) + 32 * 31;
+          const float2 *zp = Z + 32 * (31 - k2) + 31;
 #pragma unroll
           for (int g = 0; g < 4; g++) {
-            float2 pk[8];  // pk[i] = this thread's job-0 result 24 - 8 g + i
+            float2 pk[8];  // pk[i] = the partner's result 24 - 8 g + i
             tmem::ld8(taddr + 64 + 2 * (24 - 8 * g), pk);
             tmem::wait_ld8(pk);
+            if (s0) {
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const float4 f = *reinterpret_cast<const float4 *>(z16 + 32 * (31 - k2) + 24 - 8 * g + 2 * q);
+                pk[2 * q] = make_float2(f.x, f.y);
+                pk[2 * q + 1] = make_float2(f.z, f.w);
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
               const int k3 = 8 * g + j;
-              const float2 snd = s0 ? v[31 - k3] : pk[7 - j];
-              float2 rcv;
-              rcv.x = __shfl_sync(0xffffffffu, snd.x, srclane);
-              rcv.y = __shfl_sync(0xffffffffu, snd.y, srclane);
               float2 hk = k3 ? cmulc<false>(hbase, kSplitC[k3], kSplitS[k3]) : hbase;
-              float2 mine = v[k3], other = rcv;
+              float2 mine = v[k3], other = pk[7 - j];
               if (k3 < 16) {
                 rfft_pair_folded<false>(mine, other, hk, hs);
               } else {
                 rfft_pair_folded<false>(other, mine, cconj(hk), hs);
               }
-              if (s0) other = zp[-32 * k3];
+              if (s0) other = zp[-k3];
               o[1024 * k3] = mine;
               om[-1024 * k3] = other;
             }
           }
         }
       }
-      __syncthreads();  // the row buffers are free again (and Z is complete)
+      if (job == 0) __syncthreads();  // the row buffers are free again and Z is complete (job 1: m_free, and P1's barrier)
 
       if constexpr (REAL) {
         if (job == 0) {
           // row k1 = 0: X[32 m], m = k2 + 32 k3, pairs (m, 1024 - m), split in place; m = 0 is the packed (DC, Nyquist)
           // element and m = 512 is bin N/2, which the reference's split never visits (cl_fft.cpp:278).
           // Read again in job 1's pass B, several barriers from here.
-          const int m = tid;
+          const int k3 = tid & 15, k2 = tid >> 4, m = k2 + 32 * k3;  // m in [0, 512); Z is laid out [k2][k3]
           if (m == 0) {
             const float2 z0 = Z[0];
             Z[0] = make_float2((z0.x + z0.y) * hs, (z0.x - z0.y) * hs);
-            Z[512] = cscale(Z[512], scale);
+            Z[16] = cscale(Z[16], scale);  // m = 512
           } else {
-            float2 a = Z[m], b = Z[1024 - m];
+            const int pi = k2 ? 32 * (32 - k2) + 31 - k3 : 32 - k3;  // 1024 - m
+            float2 a = Z[32 * k2 + k3], b = Z[pi];
             rfft_pair_folded<false>(a, b, hw32[m], hs);
-            Z[m] = a;
-            Z[1024 - m] = b;
+            Z[32 * k2 + k3] = a;
+            Z[pi] = b;
           }
         }
       }
