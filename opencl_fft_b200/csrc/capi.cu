@@ -345,9 +345,9 @@ struct SmPlan {
       if (p) cudaFree(p);
     d_twb = d_twa = nullptr;
   }
-  template <bool INV, bool REAL>
+  template <bool INV, int KIND>
   int run(const float2 *in, float2 *out, const float2 *hw, int batch, float scale, cudaStream_t st) {
-    auto kern = fft_sm_kernel<INV, REAL>;
+    auto kern = fft_sm_kernel<INV, KIND>;
     int rc = set_smem(kern, SmGeom::SMEM);
     if (rc) return rc;
     const int g = batch < grid ? batch : grid;
@@ -663,14 +663,16 @@ struct FftPlanCore {
       return fwd ? cluster.run<false, false>(in, out, nullptr, batch, scale, st)
                  : cluster.run<true, false>(in, out, nullptr, batch, scale, st);
     if (sm.ok())
-      return fwd ? sm.run<false, false>(in, out, nullptr, batch, scale, st)
-                 : sm.run<true, false>(in, out, nullptr, batch, scale, st);
+      return fwd ? sm.run<false, kSmComplex>(in, out, nullptr, batch, scale, st)
+                 : sm.run<true, kSmComplex>(in, out, nullptr, batch, scale, st);
     if (is_large()) return large.run_c2c(!fwd, in, out, batch, scale, st);
     return launch_cfft(logn, !fwd, in, out, d_tw, batch, scale, st);
   }
   int run_real(const float2 *in, float2 *out, int batch, cudaStream_t st) {
     if (cluster.ok() && fwd) return cluster.run<false, true>(in, out, d_w2, batch, fwd_scale(), st);
-    if (sm.ok() && fwd) return sm.run<false, true>(in, out, d_hw, batch, fwd_scale(), st);
+    if (sm.ok())
+      return fwd ? sm.run<false, kSmRealFwd>(in, out, d_hw, batch, fwd_scale(), st)
+                 : sm.run<true, kSmRealInv>(in, out, d_hw, batch, 1.0f, st);
     if (is_large()) return large.run_real(!fwd, in, out, d_w2, d_hw, batch, fwd_scale(), st);
     return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, d_hw, batch, fwd_scale(), st);
   }

@@ -154,8 +154,9 @@ struct SmGeom {
   // (32 consecutive j3) are both bank-conflict free. P1 writes the row as [j2][j3] into the first 8 KiB.
   static constexpr int K2S = 32 * 8 + 16;
   static constexpr int ROW = 32 * K2S + 16;
-  static constexpr int OFF_SP = 16 * ROW;             // staging of P1's round 1, runs j1 = 16..31 (64 KiB)
-  static constexpr int OFF_Z = OFF_SP + 16 * 4096;    // row k1 = 0 of the real transform, [k2][k3] float2
+  static constexpr int RUN_C2R = 4096 + 16;           // staged bytes per run of the inverse real transform (514 columns)
+  static constexpr int OFF_SP = 16 * ROW;             // staging of P1's round 1, runs j1 = 16..31 (64 KiB + 256 B)
+  static constexpr int OFF_Z = OFF_SP + 16 * RUN_C2R; // row k1 = 0 of the real transform, [k2][k3] float2
   static constexpr int OFF_TWN = OFF_Z + 1024 * 8;    // P1 twiddle bases [5][32]: W_N^(j3 2^b)
   static constexpr int OFF_TWA = OFF_TWN + 5 * 32 * 8;  // pass-A twiddle bases [5][32]: W_1024^(j 2^b) (also W_N^(32 j2 2^b))
   static constexpr int OFF_HW = OFF_TWA + 5 * 32 * 8;   // folded split table, entries 0..1023
@@ -198,12 +199,21 @@ __device__ constexpr float kSplitS[32] = {
 // pattern (k2, k3) <-> (32 - k2, 31 - k3) and the two special elements (packed DC/Nyquist, untouched bin N/2:
 // SURVEY Q2/Q3), so it is split in an 8 KiB shared-memory buffer Z and stored by the row-16 lanes, whose partner
 // slot is free, completing the partner's lines.
-template <bool INV, bool REAL>
+//
+// Inverse real transform (KIND = 2): the unsplit of cl_fft.cpp:192-205 is fused into P1's reads. The partner of input
+// element (j1, c) is (31 - j1, 1024 - c) [(32 - j1, 0) in column 0], so the rounds are closed under c -> 1024 - c:
+// round 0 = columns [0, 256) and [768, 1024), round 1 = [256, 768); the one pair that straddles them, (256, 768), is
+// staged in both (runs of 514 columns). Every thread reads its own column and the mirrored one from the staged runs and
+// keeps its own member of each pair. In the rows, the column groups j2 are stored permuted (0..7, 24..31, 8..23) so
+// that round 0 still writes the first halves and round 1 the second.
+enum { kSmComplex = 0, kSmRealFwd = 1, kSmRealInv = 2 };
+template <bool INV, int KIND>
 __global__ void __launch_bounds__(SmGeom::THREADS, 1)
     fft_sm_kernel(const float2 *in, float2 *out, const float2 *__restrict__ twn_g, const float2 *__restrict__ twa_g,
                   const float2 *__restrict__ hw, int batch, float scale) {
   using G = SmGeom;
-  static_assert(!(REAL && INV), "the inverse real transform (unsplit first) is not built on this kernel");
+  constexpr bool REAL = (KIND == kSmRealFwd), C2R = (KIND == kSmRealInv);
+  static_assert(!(REAL && INV) && !(C2R && !INV), "the split follows a forward, the unsplit precedes an inverse transform");
   constexpr int N = G::N;
   constexpr int TCOLS = REAL ? G::TCOLS_THREAD_R : G::TCOLS_THREAD_C;
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -221,10 +231,9 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
     twn[tid] = __ldg(&twn_g[tid]);
     twa[tid] = __ldg(&twa_g[tid]);
   }
-  if constexpr (REAL) {
+  if constexpr (REAL || C2R)
     for (int i = tid; i < 1024; i += G::THREADS) hwb[i] = __ldg(&hw[i]);
-    hw32[tid] = __ldg(&hw[32 * tid]);
-  }
+  if constexpr (REAL) hw32[tid] = __ldg(&hw[32 * tid]);
   if (warp == 0) tmem::alloc((uint32_t)__cvta_generic_to_shared(misc), 4 * TCOLS);
   tmem::fence_before();
   __syncthreads();
@@ -240,13 +249,25 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   //   computed, where round 0's results do not go: runs 0..15 in the second halves of the 16 rows, runs 16..31 in
   //   a 64 KiB staging area.
   const uint32_t m_free = tma::smem_u32(misc + 2), m_full0 = tma::smem_u32(misc + 4), m_full1 = tma::smem_u32(misc + 6);
+  constexpr int RUN = C2R ? G::RUN_C2R : 4096;
+  // where run j1 of a round is staged
+  auto run_base = [&](int round, int j) -> unsigned char * {
+    return round == 0 ? rows + j * RUN : (j < 16 ? rows + j * G::ROW + 4096 : sp + (j - 16) * RUN);
+  };
   auto stage_round = [&](int round, int tn) {  // the 32 lanes of one warp, one run each
-    const float2 *nx = in + (size_t)tn * N + 1024 * lane + 512 * round;
+    const float2 *nx = in + (size_t)tn * N + 1024 * lane;
     const uint32_t mb = round ? m_full1 : m_full0;
-    unsigned char *d = round == 0 ? rows + lane * 4096 : (lane < 16 ? rows + lane * G::ROW + 4096 : sp + (lane - 16) * 4096);
-    if (lane == 0) tma::mbar_expect_tx(mb, 32 * 4096);
+    const uint32_t d = tma::smem_u32(run_base(round, lane));
+    if (lane == 0) tma::mbar_expect_tx(mb, 32 * RUN);
     __syncwarp();
-    tma::bulk_g2s(tma::smem_u32(d), nx, 4096, mb);
+    if constexpr (!C2R) {
+      tma::bulk_g2s(d, nx + 512 * round, 4096, mb);
+    } else if (round == 0) {
+      tma::bulk_g2s(d, nx, 258 * 8, mb);                   // columns [0, 258)
+      tma::bulk_g2s(d + 258 * 8, nx + 768, 256 * 8, mb);   // columns [768, 1024)
+    } else {
+      tma::bulk_g2s(d, nx + 256, 514 * 8, mb);             // columns [256, 770)
+    }
   };
   if (tid == 0) {
     tma::mbar_init(m_free, 16);
@@ -265,32 +286,59 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
     // ---- P1: radix-32 over j1 for columns c = tid, tid + 512 ------------------------------------------------------
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      const int c = tid + 512 * r;
+      // column of this thread and its position in the rows (complex / forward real: c itself)
+      const int c = !C2R ? tid + 512 * r : (r == 0 ? (tid < 256 ? tid : tid + 512) : tid + 256);
+      const int pos = !C2R ? c : (r == 0 ? tid : tid + 512);
       float2 v[32];
-      if (r == 0) {
-        tma::mbar_wait(m_full0, par);
+      tma::mbar_wait(r == 0 ? m_full0 : m_full1, par);
+      if constexpr (!C2R) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = *reinterpret_cast<const float2 *>(rows + j * 4096 + tid * 8);
-        __syncthreads();  // round 0 is in registers: the row buffers may be written, by round 1's runs too
-        if (warp == 0) stage_round(1, t);
+        for (int j = 0; j < 32; j++) v[j] = *reinterpret_cast<const float2 *>(run_base(r, j) + tid * 8);
       } else {
-        tma::mbar_wait(m_full1, par);
+        // byte offset of a column inside a staged run
+        auto off = [&](int col) { return r == 0 ? (col < 258 ? col * 8 : (col - 510) * 8) : (col - 256) * 8; };
+        const bool col0 = (c == 0);
+        const int oc = off(c), opc = off(col0 ? 0 : 1024 - c), pj0 = col0 ? 32 : 31;
+        const float2 hbase = hwb[c];
+        float2 raw0 = make_float2(0.f, 0.f), raw16 = raw0;
 #pragma unroll
-        for (int j = 0; j < 32; j++)
-          v[j] = *reinterpret_cast<const float2 *>((j < 16 ? rows + j * G::ROW + 4096 : sp + (j - 16) * 4096) + tid * 8);
-        __syncthreads();  // round 1 is in registers: the second halves of the rows may be written
+        for (int j = 0; j < 32; j++) {
+          const float2 a = *reinterpret_cast<const float2 *>(run_base(r, j) + oc);
+          // partner run 31 - j (32 - j in column 0: a different run per lane there, so the address is computed)
+          const int pj = (pj0 - j) & 31;
+          const unsigned char *pb = r == 0 ? rows + pj * RUN : (pj < 16 ? rows + pj * G::ROW + 4096 : sp + (pj - 16) * RUN);
+          const float2 b = *reinterpret_cast<const float2 *>(pb + opc);
+          if (j == 0) raw0 = a;
+          if (j == 16) raw16 = a;
+          // hw(1024 j + c) = hw(c) exp(+i pi j / 32), extended analytically past N/2, where hw(N - i) = conj(hw(i))
+          const float2 hk = j ? cmulc<true>(hbase, kSplitC[j], kSplitS[j]) : hbase;
+          float2 A = a, B = b;
+          if (j < 16) {
+            rfft_pair_folded<true>(A, B, hk, 0.5f);
+            v[j] = A;
+          } else {
+            rfft_pair_folded<true>(B, A, cconj(hk), 0.5f);
+            v[j] = A;
+          }
+        }
+        if (col0) {  // element 0: packed (DC, Nyquist); element N/2: never visited by the reference (cl_fft.cpp:286)
+          v[0] = rfft_dc<true>(raw0);
+          v[16] = raw16;
+        }
       }
-      // W_N^(c 2^b), c = 32 j2 + j3 (j2 = warp + 16 r, j3 = lane), as the product of two table entries
+      __syncthreads();  // the round is in registers: its half of the row buffers may be written
+      if (r == 0 && warp == 0) stage_round(1, t);
+      // W_N^(c 2^b), c = 32 j2 + j3, as the product of two table entries
       float2 base[5];
 #pragma unroll
       for (int b = 0; b < 5; b++) {
-        base[b] = cmul(twa[b * 32 + warp + 16 * r], twn[b * 32 + lane]);
+        base[b] = cmul(twa[b * 32 + (c >> 5)], twn[b * 32 + (c & 31)]);
         if (INV) base[b].y = -base[b].y;
       }
       dft32<INV>(v);
       tw_tree<4, 0, false>(v, make_float2(1.f, 0.f), base);
 #pragma unroll
-      for (int s = 0; s < 16; s++) *reinterpret_cast<float2 *>(rows + s * G::ROW + c * 8) = v[s];
+      for (int s = 0; s < 16; s++) *reinterpret_cast<float2 *>(rows + s * G::ROW + pos * 8) = v[s];
 #pragma unroll
       for (int g = 0; g < 2; g++) {
         float2 h8[8];
@@ -335,7 +383,10 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
         unsigned char *row = rows + warp * G::ROW;
         float2 v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = *reinterpret_cast<const float2 *>(row + (j * 32 + lane) * 8);
+        for (int j = 0; j < 32; j++) {
+          const int pj = !C2R ? j : (j < 8 ? j : (j >= 24 ? j - 16 : j + 8));  // where column group j2 = j is stored
+          v[j] = *reinterpret_cast<const float2 *>(row + (pj * 32 + lane) * 8);
+        }
         float2 base[5];
 #pragma unroll
         for (int b = 0; b < 5; b++) {
@@ -411,7 +462,7 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
           }
           __syncwarp();
           float2 *om = dst + (N - (k1 + 32 * k2)) - (s0 ? 16 : 0);
-          const float2 *zp = Z + 32 * (31 - k2) + 31;
+          const float2 *zp = Z + 32 * (31 - k2);
 #pragma unroll
           for (int g = 0; g < 4; g++) {
             float2 pk[8];  // pk[i] = the partner's result 24 - 8 g + i
@@ -428,16 +479,26 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
 #pragma unroll
             for (int j = 0; j < 8; j++) {
               const int k3 = 8 * g + j;
-              float2 hk = k3 ? cmulc<false>(hbase, kSplitC[k3], kSplitS[k3]) : hbase;
-              float2 mine = v[k3], other = pk[7 - j];
+              const float2 hk = k3 ? cmulc<false>(hbase, kSplitC[k3], kSplitS[k3]) : hbase;
               if (k3 < 16) {
-                rfft_pair_folded<false>(mine, other, hk, hs);
+                rfft_pair_folded<false>(v[k3], pk[7 - j], hk, hs);
               } else {
-                rfft_pair_folded<false>(other, mine, cconj(hk), hs);
+                rfft_pair_folded<false>(pk[7 - j], v[k3], cconj(hk), hs);
               }
-              if (s0) other = zp[-k3];
-              o[1024 * k3] = mine;
-              om[-1024 * k3] = other;
+            }
+            if (s0) {  // partner slot of the row-16 lanes: row 0, elements (31 - k2, 24 - 8 g + i)
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const float4 f = *reinterpret_cast<const float4 *>(zp + 24 - 8 * g + 2 * q);
+                pk[2 * q] = make_float2(f.x, f.y);
+                pk[2 * q + 1] = make_float2(f.z, f.w);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int k3 = 8 * g + j;
+              o[1024 * k3] = v[k3];
+              om[-1024 * k3] = pk[7 - j];
             }
           }
         }

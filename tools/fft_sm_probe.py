@@ -17,7 +17,7 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--modes", default="0,1")
 ap.add_argument("--check-batch", type=int, default=300)
 ap.add_argument("--skip-check", action="store_true")
-ap.add_argument("--kinds", default="r2c,c2c")
+ap.add_argument("--kinds", default="r2c,c2c,c2r")
 args = ap.parse_args()
 peak = 6544.7
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -70,6 +70,17 @@ for mode in [int(m) for m in args.modes.split(",")]:
         assert f.transform_dev(d, d, cb) == 0  # in place
         torch.cuda.synchronize()
         res["r2c_inplace_same"] = bool(np.array_equal(d.cpu().numpy().view(np.complex64), got))
+        # inverse real transform of every spectrum gives the signal back
+        iv = eng.Clrfft(0, size, False, max_batch=cb)
+        ds = torch.from_numpy(got.view(np.float32).copy()).cuda()
+        ob = torch.empty(cb, size, device="cuda")
+        assert iv.transform_dev(ds, ob, cb) == 0
+        torch.cuda.synchronize()
+        back = ob.cpu().numpy()
+        err = np.linalg.norm(back - xr, axis=1) / np.linalg.norm(xr, axis=1)
+        res["c2r_err_max"] = float(err.max())
+        res["c2r_bad"] = int((err > 2e-6).sum())
+        iv.close()
         f.close()
         for fwd, want, key in ((True, want_c, "c2c_fwd"), (False, want_ci, "c2c_inv")):
             pl = eng.Clcfft(0, size // 2, fwd, max_batch=cb)
@@ -85,7 +96,7 @@ for mode in [int(m) for m in args.modes.split(",")]:
     # timing
     for kind in args.kinds.split(","):
         batch = args.batch if kind == "r2c" else args.batch
-        plan = eng.Clrfft(0, size, True, max_batch=batch) if kind == "r2c" else eng.Clcfft(0, size // 2, True, max_batch=batch)
+        plan = eng.Clrfft(0, size, kind == "r2c", max_batch=batch) if kind != "c2c" else eng.Clcfft(0, size // 2, True, max_batch=batch)
         k = [0]
 
         def fn():
