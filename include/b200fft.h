@@ -53,6 +53,28 @@ const char *b2f_last_cuda_error(void);
 /* library version string, e.g. "b200fft 0.1 (sm_100a)" */
 const char *b2f_version(void);
 
+/* ---- options ---------------------------------------------------------------------------------
+ * Re-measurement knobs: process-wide defaults that a handle COPIES when it is created; no entry
+ * point consults them (or the environment) afterwards. Initial values come from the environment
+ * variables B2F_<NAME IN CAPITALS>, read once before the first create. The reference has no
+ * runtime configuration: the constructor arguments stay the only per-object input and
+ * every default below is the measured winner.
+ *   fft_sm_min_batch  96     N = 32768 complex / 65536 real: the one-SM kernel from this batch up
+ *                            (0 never, 1 always); below it the four-step launch pair
+ *   large_chunk_mb    256    scratch chunk of the four-step launch pair
+ *   rows_rb16         0      16-row CTAs in the four-step real rows kernel
+ *   separate_split    0      unfused real split / unsplit pass on the four-step path
+ *   pconv_tma         -1     partitioned-convolution MAC feed: -1 measured choice, 0 registers, 1 TMA
+ *   pconv_cluster     0      cluster split of the partitions: 0 measured choice, else 1 | 2 | 4 | 8
+ *                            (anything else, or more than nparts: create fails with INVALID_VALUE)
+ *   pconv_pipeline    1      two-stream host call for >= 128 channels
+ *   zerocopy_max      65536  host calls moving at most this many bytes run on pinned buffers directly
+ *   graph             1      CUDA graph replay for the multi-launch host paths (pts >= 8192)
+ *   verbose           0
+ * Unknown names return B2F_ERR_INVALID_VALUE. */
+int b2f_set_option(const char *name, long long value);
+int b2f_get_option(const char *name, long long *value);
+
 /* ---- devices (replaces clGetDeviceIDs / clGetDeviceInfo as used at test_cfft.cpp:31-38,
  *      csound/opcode.cpp:57-61) ------------------------------------------------------------- */
 int b2f_device_count(int *count);
@@ -96,14 +118,23 @@ typedef struct b2f_pconv b2f_pconv;
 int b2f_pconv_create(b2f_pconv **h, int device, int cvs, int pts, int channels);
 int b2f_pconv_destroy(b2f_pconv *h);
 int b2f_pconv_nparts(const b2f_pconv *h);
-/* zero the delay line, the overlap tail and the ring positions (IR spectra are kept) */
+/* Zero the delay line and the overlap tail and put both ring positions back to their start
+ * (wp = 0, wp2 = nparts - 1, cl_conv.cpp:144). The IR spectra are KEPT, frame for frame: after
+ * static push_ir that is the pushed IR; after time-varying use it is whatever the ring held, which
+ * later time-varying blocks re-record from frame nparts - 1 downwards exactly as a fresh object
+ * would. Waits for the handle's own streams; work queued through *_dev entry points on a
+ * caller's stream must have been synchronised by the caller. Clears a sticky failure (below). */
 int b2f_pconv_reset(b2f_pconv *h);
 /* Clpconv::push_ir (cl_conv.cpp:353-388). ir: per channel nparts*pts floats, channel c starting
  * at ir + c*ir_stride (ir_stride in floats; pass cvs for back-to-back IRs). */
 int b2f_pconv_push_ir_host(b2f_pconv *h, const float *ir, size_t ir_stride);
 int b2f_pconv_push_ir_dev(b2f_pconv *h, const void *d_ir, size_t ir_stride, void *stream);
 /* Clpconv::convolution(out, in) (cl_conv.cpp:393-458): one block of pts samples per channel.
- * in/out: [channels][pts] floats. */
+ * in/out: [channels][pts] floats.
+ * Stream ordering: a handle's state is advanced by every call, *_host calls on the handle's own
+ * stream(s), *_dev calls on the caller's; the caller orders the two kinds (synchronise the stream
+ * before switching). If a multi-stream host call fails half way the handle turns FAILED -- every
+ * later process call returns the same code -- until b2f_pconv_reset(). */
 int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in);
 int b2f_pconv_process_dev(b2f_pconv *h, void *d_out, const void *d_in, void *stream);
 /* Clpconv::convolution(out, in1, in2) (cl_conv.cpp:460-548): time-varying; in2's block is

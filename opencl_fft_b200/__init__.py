@@ -29,7 +29,24 @@ from ._capi import B2fError, error_string, last_cuda_error, lib  # noqa: F401
 PI = 3.141592653589793  # cl_fft::PI, reference cl_fft.h:24
 
 __all__ = ["Clcfft", "Clrfft", "Clpconv", "Cldconv", "device_count", "device_name", "cl_error_string",
-           "B2fError", "PI"]
+           "B2fError", "PI", "set_option", "get_option"]
+
+INVALID_VALUE = 2  # B2F_ERR_INVALID_VALUE
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide default copied by handles created afterwards (include/b200fft.h lists the names)."""
+    rc = lib().b2f_set_option(name.encode(), int(value))
+    if rc:
+        raise B2fError(rc, f"b2f_set_option({name})")
+
+
+def get_option(name: str) -> int:
+    v = C.c_longlong(0)
+    rc = lib().b2f_get_option(name.encode(), C.byref(v))
+    if rc:
+        raise B2fError(rc, f"b2f_get_option({name})")
+    return v.value
 
 
 def cl_error_string(err: int) -> str:
@@ -98,7 +115,7 @@ class Clcfft:
         if self._err:
             return self._err
         if c.size % self.N:
-            return _capi.lib().b2f_cfft_exec_host(self._h, None, 1)  # -> invalid value
+            return INVALID_VALUE
         return lib().b2f_cfft_exec_host(self._h, c.ctypes.data, c.size // self.N)
 
     def transform_dev(self, d_in, d_out, batch: int, stream=None) -> int:
@@ -136,8 +153,8 @@ class Clrfft:
         if self._err:
             return self._err
         rp = c.ctypes.data if r is None else _host(r, np.float32, "r").ctypes.data
-        if c.size % self.N:
-            return lib().b2f_rfft_exec_host(self._h, None, None, 1)
+        if c.size % self.N or (r is not None and r.size != 2 * c.size):
+            return INVALID_VALUE  # the engine would read / write size reals per transform behind r
         return lib().b2f_rfft_exec_host(self._h, c.ctypes.data, rp, c.size // self.N)
 
     def transform_dev(self, d_in, d_out, batch: int, stream=None) -> int:
@@ -181,12 +198,20 @@ class Clpconv:
         """ir: [channels][>= nparts*pts] float32 (row stride = ir.shape[-1])."""
         ir = _host(ir, np.float32, "ir")
         stride = ir.shape[-1] if ir.ndim > 1 else ir.size // self.channels
+        # the engine reads nparts*pts floats from each of `channels` rows `stride` apart
+        if stride < self.nparts * self.pts or ir.size < (self.channels - 1) * stride + self.nparts * self.pts:
+            self._err = INVALID_VALUE
+            return self._err
         self._err = lib().b2f_pconv_push_ir_host(self._h, ir.ctypes.data, stride)
         return self._err
 
     def convolution(self, output: np.ndarray, input1: np.ndarray, input2: np.ndarray | None = None) -> int:
         out = _host(output, np.float32, "output")
         a = _host(input1, np.float32, "input1")
+        need = self.channels * self.pts  # one block per channel is read and written
+        if out.size < need or a.size < need or (input2 is not None and np.size(input2) < need):
+            self._err = INVALID_VALUE
+            return self._err
         if input2 is None:
             self._err = lib().b2f_pconv_process_host(self._h, out.ctypes.data, a.ctypes.data)
         else:
@@ -249,12 +274,18 @@ class Cldconv:
     def push_ir(self, ir: np.ndarray) -> int:
         ir = _host(ir, np.float32, "ir")
         stride = ir.shape[-1] if ir.ndim > 1 else ir.size // self.channels
+        if stride < self.irsize or ir.size < (self.channels - 1) * stride + self.irsize:
+            return INVALID_VALUE
         return lib().b2f_dconv_push_ir_host(self._h, ir.ctypes.data, stride)
 
     def convolution(self, output: np.ndarray, input1: np.ndarray, input2: np.ndarray | None = None,
                     nblocks: int = 1) -> int:
         out = _host(output, np.float32, "output")
         a = _host(input1, np.float32, "input1")
+        need = self.channels * (nblocks if input2 is None else 1) * self.vsize
+        if nblocks < 1 or out.size < need or a.size < need or (input2 is not None and np.size(input2) < need):
+            self._err = INVALID_VALUE
+            return self._err
         if input2 is None:
             self._err = lib().b2f_dconv_process_host(self._h, out.ctypes.data, a.ctypes.data, nblocks)
         else:

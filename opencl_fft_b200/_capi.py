@@ -15,6 +15,8 @@ SYMBOLS = {
     "b2f_error_string": (C.c_char_p, [_i]),
     "b2f_last_cuda_error": (C.c_char_p, []),
     "b2f_version": (C.c_char_p, []),
+    "b2f_set_option": (_i, [C.c_char_p, C.c_longlong]),
+    "b2f_get_option": (_i, [C.c_char_p, C.POINTER(C.c_longlong)]),
     "b2f_device_count": (_i, [C.POINTER(_i)]),
     "b2f_device_name": (_i, [_i, C.c_char_p, _sz]),
     "b2f_cfft_create": (_i, [_pp, _i, _i, _i, _i]),

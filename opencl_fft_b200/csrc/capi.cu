@@ -12,13 +12,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/b200fft.h"
 #include "dconv_kernels.cuh"
-#include "fft_cluster.cuh"
 #include "fft_kernels.cuh"
 #include "fft_large.cuh"
 #include "fft_sm.cuh"
@@ -58,6 +59,74 @@ extern "C" const char *b2f_error_string(int code) {
 extern "C" const char *b2f_last_cuda_error(void) { return g_cuda_err.c_str(); }
 extern "C" const char *b2f_version(void) { return "b200fft 0.1 (sm_100a)"; }
 
+// ---- options ----------------------------------------------------------------------------------------
+// Re-measurement knobs. They are process-wide DEFAULTS that a handle copies when it is created: no entry point
+// reads the environment or this table afterwards, so a running handle never changes behaviour behind the
+// caller's back. Initial values come from the B2F_* environment variables, read once, before the first create;
+// b2f_set_option() changes them for handles created later (include/b200fft.h lists the names).
+struct Options {
+  long long fft_sm_min_batch = 96;   // N = 2^15: one-SM kernel from this batch up (0: never, 1: always)
+  long long large_chunk_mb = 256;    // scratch chunk of the four-step launch pair
+  long long rows_rb16 = 0;           // 16-row CTAs in the real rows kernel
+  long long separate_split = 0;      // unfused real split / unsplit pass (four-step path)
+  long long pconv_tma = -1;          // MAC feed of the partitioned convolution: -1 measured choice, 0 registers, 1 TMA
+  long long pconv_cluster = 0;       // cluster split of the partitions: 0 measured choice, else 1 / 2 / 4 / 8
+  long long pconv_pipeline = 1;      // two-stream host call for many channels
+  long long zerocopy_max = 65536;    // host calls up to this many bytes run on the pinned buffers directly
+  long long graph = 1;               // CUDA graph for the multi-launch host paths
+  long long verbose = 0;
+};
+struct OptionName {
+  const char *name, *env;
+  long long Options::*field;
+};
+static const OptionName kOptionNames[] = {
+    {"fft_sm_min_batch", "B2F_FFT_SM_MIN_BATCH", &Options::fft_sm_min_batch},
+    {"large_chunk_mb", "B2F_LARGE_CHUNK_MB", &Options::large_chunk_mb},
+    {"rows_rb16", "B2F_ROWS_RB16", &Options::rows_rb16},
+    {"separate_split", "B2F_SEPARATE_SPLIT", &Options::separate_split},
+    {"pconv_tma", "B2F_PCONV_TMA", &Options::pconv_tma},
+    {"pconv_cluster", "B2F_PCONV_CLUSTER", &Options::pconv_cluster},
+    {"pconv_pipeline", "B2F_PCONV_PIPELINE", &Options::pconv_pipeline},
+    {"zerocopy_max", "B2F_ZEROCOPY_MAX", &Options::zerocopy_max},
+    {"graph", "B2F_GRAPH", &Options::graph},
+    {"verbose", "B2F_VERBOSE", &Options::verbose},
+};
+static std::mutex g_opt_mutex;
+static Options &options_locked() {
+  static Options o = [] {
+    Options v;
+    for (const OptionName &n : kOptionNames)
+      if (const char *e = getenv(n.env)) v.*(n.field) = atoll(e);
+    return v;
+  }();
+  return o;
+}
+static Options current_options() {
+  std::lock_guard<std::mutex> lk(g_opt_mutex);
+  return options_locked();
+}
+extern "C" int b2f_set_option(const char *name, long long value) {
+  if (!name) return B2F_ERR_INVALID_VALUE;
+  std::lock_guard<std::mutex> lk(g_opt_mutex);
+  for (const OptionName &n : kOptionNames)
+    if (!strcmp(name, n.name)) {
+      options_locked().*(n.field) = value;
+      return B2F_OK;
+    }
+  return B2F_ERR_INVALID_VALUE;
+}
+extern "C" int b2f_get_option(const char *name, long long *value) {
+  if (!name || !value) return B2F_ERR_INVALID_VALUE;
+  std::lock_guard<std::mutex> lk(g_opt_mutex);
+  for (const OptionName &n : kOptionNames)
+    if (!strcmp(name, n.name)) {
+      *value = options_locked().*(n.field);
+      return B2F_OK;
+    }
+  return B2F_ERR_INVALID_VALUE;
+}
+
 extern "C" int b2f_device_count(int *count) {
   if (!count) return B2F_ERR_INVALID_VALUE;
   *count = 0;
@@ -74,9 +143,12 @@ extern "C" int b2f_device_name(int device, char *buf, size_t buflen) {
 
 // Make `device` current for the duration of an entry point and put the caller's device back afterwards: the
 // library must not change the calling thread's current device behind the application's (or torch's) back.
+static thread_local int g_device = -1;  // the device the running entry point made current (set_smem's cache key)
 struct DeviceGuard {
-  int prev = -1, rc = B2F_OK;
+  int prev = -1, rc = B2F_OK, prev_g = -1;
   explicit DeviceGuard(int device) {
+    prev_g = g_device;
+    g_device = device;
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     if (prev != device) {
       cudaError_t e = cudaSetDevice(device);
@@ -90,6 +162,7 @@ struct DeviceGuard {
     }
   }
   ~DeviceGuard() {
+    g_device = prev_g;
     if (prev >= 0 && cudaSetDevice(prev) != cudaSuccess) (void)cudaGetLastError();
   }
 };
@@ -154,10 +227,25 @@ static int upload(const std::vector<float2> &h, float2 **d) {
 }
 
 // ---- kernel dispatch ----------------------------------------------------------------------------------
+// Opt a kernel in to more than 48 KB of dynamic shared memory: once per (kernel, device), not once per launch --
+// cudaFuncSetAttribute costs about as much as the launch itself on the single-block latency path.
+static int set_smem_once(const void *fn, int bytes) {
+  static std::mutex m;
+  static std::unordered_map<uint64_t, int> done;
+  const uint64_t key = (uint64_t)(uintptr_t)fn * 64u + (uint64_t)(g_device < 0 ? 63 : g_device & 63);
+  {
+    std::lock_guard<std::mutex> lk(m);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return B2F_OK;
+  }
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  std::lock_guard<std::mutex> lk(m);
+  done[key] = bytes;
+  return B2F_OK;
+}
 template <class K>
 static int set_smem(K kernel, int bytes) {
-  if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  return B2F_OK;
+  return bytes > 48 * 1024 ? set_smem_once((const void *)kernel, bytes) : B2F_OK;
 }
 
 template <int LOGN>
@@ -243,88 +331,15 @@ static int launch_rfft(int logn, bool inv, const float2 *in, float2 *out, const 
 }
 
 
-// ---- cluster plan (fft_cluster.cuh): N = N1 * 16 on persistent 4-CTA clusters -------------------------------
-struct ClusterPlan {
-  int logn = 0, log1 = 0, max_clusters = 0;
-  float2 *d_ctw1 = nullptr, *d_ctwl = nullptr;  // N1-point pass twiddles, [16][N1] inter-step table
-  bool ok() const { return d_ctwl != nullptr; }
-  // Off by default: on B200 the two-kernel four-step path (fft_large.cuh) measures faster for every transform
-  // this kernel covers (real forward 2^15: 2.29 vs 2.11 TB/s; complex 2^15: 2.96 vs 2.05). Kept as the
-  // single-HBM-pass design to come back to (profiles/r01_fft_cluster_notes.md); B2F_CLUSTER_FFT=1 enables it
-  // for N = 2^15, B2F_CLUSTER_FFT_MIN_LOGN=13|14 extends it downwards.
-  static bool wanted(int logn) {
-    if (!getenv("B2F_CLUSTER_FFT") && !getenv("B2F_CLUSTER_FFT_MIN_LOGN")) return false;
-    const char *lo = getenv("B2F_CLUSTER_FFT_MIN_LOGN");
-    const int min_logn = lo ? atoi(lo) : 15;
-    return logn >= min_logn && logn >= 13 && logn <= 15;
-  }
-  int init(int logn_) {
-    logn = logn_;
-    log1 = logn - 4;
-    const int N = 1 << logn, CN1 = 1 << log1;
-    int rc;
-    if ((rc = upload(make_pass_twiddles(log1), &d_ctw1))) return rc;
-    std::vector<float2> t((size_t)N);
-    for (int k1 = 0; k1 < CN1; k1++)
-      for (int n2 = 0; n2 < 16; n2++) t[(size_t)n2 * CN1 + k1] = ref_twiddle((long long)n2 * k1, N);
-    return upload(t, &d_ctwl);
-  }
-  void destroy() {
-    if (d_ctw1) cudaFree(d_ctw1);
-    if (d_ctwl) cudaFree(d_ctwl);
-    d_ctw1 = d_ctwl = nullptr;
-  }
-  // one persistent 4-CTA cluster per 4 SMs, looping over the batch
-  template <int L1, bool INV, bool REAL>
-  int run_cluster_t(const float2 *in, float2 *out, const float2 *w2, int batch, float scale, cudaStream_t st) {
-    using C = ClusterGeom<L1>;
-    auto kern = fft_cluster_kernel<L1, INV, REAL>;
-    int rc = set_smem(kern, C::SMEM_BYTES);
-    if (rc) return rc;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(C::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = C::S;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (max_clusters == 0) {
-      cfg.gridDim = dim3(C::S * 64, 1, 1);
-      int n = 0;
-      CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-      max_clusters = n > 0 ? n : 1;
-    }
-    const int ncl = batch < max_clusters ? batch : max_clusters;
-    cfg.gridDim = dim3(C::S * ncl, 1, 1);
-    CK(cudaLaunchKernelEx(&cfg, kern, in, out, (const float2 *)d_ctw1, (const float2 *)d_ctwl, w2, batch, scale));
-    return B2F_OK;
-  }
-  template <bool INV, bool REAL>
-  int run(const float2 *in, float2 *out, const float2 *w2, int batch, float scale, cudaStream_t st) {
-    switch (log1) {
-      case 9: return run_cluster_t<9, INV, REAL>(in, out, w2, batch, scale, st);
-      case 10: return run_cluster_t<10, INV, REAL>(in, out, w2, batch, scale, st);
-      case 11: return run_cluster_t<11, INV, REAL>(in, out, w2, batch, scale, st);
-      default: return B2F_ERR_UNSUPPORTED;
-    }
-  }
-};
-
 // ---- one-SM plan (fft_sm.cuh): N = 2^15 in one pass over HBM, one persistent CTA per SM ------------------------------
 struct SmPlan {
   int grid = 0;
   float2 *d_twb = nullptr, *d_twa = nullptr;
   bool ok() const { return d_twb != nullptr; }
-  // B2F_FFT_SM=0 (read when the plan is created) selects the four-step launch pair of fft_large.cuh instead
-  static bool wanted(int logn) {
-    if (logn != SmGeom::LOGN) return false;
-    const char *e = getenv("B2F_FFT_SM");
-    return !(e && atoi(e) == 0);
-  }
+  // A transform takes one SM ~25 us whatever the batch, so below ~100 transforms the four-step launch pair, which
+  // spreads every transform over the whole GPU, is the faster one (measured crossover, tools/fft_sm_probe.py).
+  long long min_batch = 96;
+  bool use_for(int batch) const { return ok() && min_batch > 0 && batch >= min_batch; }
   int init(int device) {
     const int N = SmGeom::N;
     std::vector<float2> twn(5 * 32), twa(5 * 32);
@@ -369,7 +384,9 @@ struct LargePlan {
   // stores. 256 MB per launch pair is where that saturates (complex 2048 x 32768: 0.369 ms at 256 MB and at
   // 1 GiB; real: 0.434 vs 0.463 ms, the rows kernel walks its chunk backwards and finds the tail in L2).
   static constexpr size_t kScratchBytes = 256u << 20;
-  int init(int logn_, int max_batch) {
+  Options opt;
+  int init(int logn_, int max_batch, const Options &o) {
+    opt = o;
     logn = logn_;
     log1 = logn / 2;
     log2 = logn - log1;
@@ -381,8 +398,7 @@ struct LargePlan {
     for (int k1 = 0; k1 < N1; k1++)
       for (int n2 = 0; n2 < N2; n2++) twl[(size_t)k1 * N2 + n2] = ref_twiddle((long long)n2 * k1, N);
     if ((rc = upload(twl, &d_twl))) return rc;
-    size_t scratch_bytes = kScratchBytes;
-    if (const char *e = getenv("B2F_LARGE_CHUNK_MB")) scratch_bytes = (size_t)atoll(e) << 20;  // re-measurement knob
+    const size_t scratch_bytes = opt.large_chunk_mb > 0 ? (size_t)opt.large_chunk_mb << 20 : kScratchBytes;
     chunk = (int)(scratch_bytes / ((size_t)N * sizeof(float2)));
     if (chunk < 1) chunk = 1;
     if (chunk > max_batch) chunk = max_batch < 1 ? 1 : max_batch;
@@ -393,9 +409,9 @@ struct LargePlan {
     return B2F_OK;
   }
   void destroy() {
-    for (void *p : {(void *)d_tw1, (void *)d_tw2, (void *)d_twl, (void *)d_scratch, (void *)d_fscratch})
+    for (void *p : {(void *)d_tw1, (void *)d_tw2, (void *)d_twl, (void *)d_scratch})
       if (p) cudaFree(p);
-    d_tw1 = d_tw2 = d_twl = d_scratch = d_fscratch = nullptr;
+    d_tw1 = d_tw2 = d_twl = d_scratch = nullptr;
   }
   // UNSPLIT: inverse real transform, the unsplit fused into the columns kernel (hw = folded inverse split table)
   template <int L1, int L2, bool INV, bool REAL, int RBT, bool UNSPLIT = false>
@@ -431,63 +447,11 @@ struct LargePlan {
   int run_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw = nullptr) {
     constexpr int RB = LargeGeom<L1, L2>::RB;
     if constexpr (REAL) {
-      static const bool rb16 = getenv("B2F_ROWS_RB16") != nullptr;
-      if (!rb16) return run_tt<L1, L2, INV, true, 2 * RB>(in, out, batch, scale, st, hw);
+      if (!opt.rows_rb16) return run_tt<L1, L2, INV, true, 2 * RB>(in, out, batch, scale, st, hw);
     }
     return run_tt<L1, L2, INV, REAL, RB>(in, out, batch, scale, st, hw);
   }
-  // Both steps in one launch on 8-CTA clusters with cluster-private, L2-resident scratch (fft_large.cuh,
-  // large_fused_kernel): N = 2^15 only (8 column groups == 8 row groups == the portable cluster size).
-  // B2F_LARGE_TWO_KERNEL=1 selects the two-launch path instead.
-  float2 *d_fscratch = nullptr;
-  int fused_clusters = 0;
-  bool fused_wanted() const { return logn == 15 && getenv("B2F_LARGE_FUSED") && !getenv("B2F_LARGE_TWO_KERNEL"); }
-  template <int L1, int L2, bool INV, bool REAL, int MINB>
-  int run_fused_tt(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw) {
-    using L = LargeGeom<L1, L2>;
-    auto kern = large_fused_kernel<L1, L2, INV, REAL, MINB>;
-    const int smem = FusedGeom<L1, L2>::SMEM_BYTES;
-    int rc = set_smem(kern, smem);
-    if (rc) return rc;
-    cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(L::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 8;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (fused_clusters == 0) {
-      cfg.gridDim = dim3(8 * 64, 1, 1);
-      int n = 0;
-      CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-      if (getenv("B2F_VERBOSE")) fprintf(stderr, "b200fft: fused large FFT, %d resident 8-CTA clusters\n", n);
-      if (const char *e = getenv("B2F_FUSED_CLUSTERS")) n = atoi(e) > 0 ? atoi(e) : n;
-      fused_clusters = n > 0 ? n : 1;
-      CK(cudaMalloc((void **)&d_fscratch, (size_t)fused_clusters * FusedGeom<L1, L2>::NBUF * L::N * sizeof(float2)));
-    }
-    const int ncl = batch < fused_clusters ? batch : fused_clusters;
-    cfg.gridDim = dim3(8 * ncl, 1, 1);
-    CK(cudaLaunchKernelEx(&cfg, kern, in, out, d_fscratch, (const float2 *)d_tw1, (const float2 *)d_tw2,
-                          (const float2 *)d_twl, hw, batch, scale));
-    return B2F_OK;
-  }
-  template <int L1, int L2, bool INV, bool REAL>
-  int run_fused_t(const float2 *in, float2 *out, int batch, float scale, cudaStream_t st, const float2 *hw) {
-    static const int minb = [] {
-      const char *e = getenv("B2F_FUSED_MINB");
-      return e ? atoi(e) : 2;
-    }();
-    return minb >= 3 ? run_fused_tt<L1, L2, INV, REAL, 3>(in, out, batch, scale, st, hw)
-                     : run_fused_tt<L1, L2, INV, REAL, 2>(in, out, batch, scale, st, hw);
-  }
   int run_c2c(bool inv, const float2 *in, float2 *out, int batch, float scale, cudaStream_t st) {
-    if (fused_wanted())
-      return inv ? run_fused_t<7, 8, true, false>(in, out, batch, scale, st, nullptr)
-                 : run_fused_t<7, 8, false, false>(in, out, batch, scale, st, nullptr);
     if (logn == 15) return inv ? run_t<7, 8, true>(in, out, batch, scale, st) : run_t<7, 8, false>(in, out, batch, scale, st);
     if (logn == 16) return inv ? run_t<8, 8, true>(in, out, batch, scale, st) : run_t<8, 8, false>(in, out, batch, scale, st);
     return B2F_ERR_UNSUPPORTED;
@@ -495,12 +459,11 @@ struct LargePlan {
   int run_real(bool inv, const float2 *in, float2 *out, const float2 *w2, const float2 *hw, int batch, float fwd_scale,
                cudaStream_t st) {
     const int N = 1 << logn;
-    if (!inv && !getenv("B2F_SEPARATE_SPLIT")) {  // forward: split fused into the rows kernel
-      if (fused_wanted()) return run_fused_t<7, 8, false, true>(in, out, batch, fwd_scale, st, hw);
+    if (!inv && !opt.separate_split) {  // forward: split fused into the rows kernel
       if (logn == 15) return run_t<7, 8, false, true>(in, out, batch, fwd_scale, st, hw);
       if (logn == 16) return run_t<8, 8, false, true>(in, out, batch, fwd_scale, st, hw);
     }
-    if (inv && !getenv("B2F_SEPARATE_SPLIT") && !fused_wanted()) {  // inverse: unsplit fused into the columns kernel
+    if (inv && !opt.separate_split) {  // inverse: unsplit fused into the columns kernel
       if (logn == 15) return run_tt<7, 8, true, false, LargeGeom<7, 8>::RB, true>(in, out, batch, 1.0f, st, hw);
       if (logn == 16) return run_tt<8, 8, true, false, LargeGeom<8, 8>::RB, true>(in, out, batch, 1.0f, st, hw);
     }
@@ -551,15 +514,7 @@ static const size_t kBounceMax = 1u << 20;
 // many bytes each way (one block of a few channels, one small transform -- what a Csound performance thread
 // does every k-cycle), the kernel reads its input from and writes its result to the PINNED bounce buffers
 // directly (they are device-accessible under unified addressing), so the call is: memcpy in, ONE launch,
-// one stream synchronise, memcpy out -- no DMA copies to set up and wait for. B2F_ZEROCOPY_MAX=0 disables it.
-static size_t zerocopy_max() {
-  static size_t v = [] {
-    const char *e = getenv("B2F_ZEROCOPY_MAX");
-    return e ? (size_t)atoll(e) : (size_t)65536;
-  }();
-  return v;
-}
-
+// one stream synchronise, memcpy out -- no DMA copies to set up and wait for. The threshold is the `zerocopy_max` option (0 disables the path).
 static int h2d(void *dst, const void *src, size_t bytes, Staging &sg, cudaStream_t st) {
   if (bytes <= kBounceMax) {
     int rc = sg.ensure(bytes);
@@ -598,30 +553,28 @@ struct FftPlanCore {
   float2 *d_hw = nullptr;   // folded split table 0.5*scale*i*w2 (forward) / its conjugate, unscaled (inverse)
   float2 *d_buf = nullptr;  // device buffer backing the host entry points
   LargePlan large;          // N > 2^kMaxSmemLogN
-  ClusterPlan cluster;      // N = 2^13..2^15 on thread-block clusters (when selected)
   SmPlan sm;                // N = 2^15: one pass over HBM, one transform per SM (fft_sm.cuh)
   cudaStream_t stream = nullptr;
   Staging sg_in, sg_out;
+  Options opt;
   bool is_large() const { return logn > kMaxSmemLogN; }
   int init(int dev, int n, int f, int mb, bool real) {
     device = dev, N = n, fwd = f ? 1 : 0, max_batch = mb < 1 ? 1 : mb;
     logn = ilog2_exact(n);
+    opt = current_options();
     int rc = check_device(dev);
     if (rc) return rc;
     B2F_ON_DEVICE(dev);
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (is_large()) {
-      rc = large.init(logn, max_batch);
+      rc = large.init(logn, max_batch, opt);
       if (rc) return rc;
     } else {
       rc = upload(make_pass_twiddles(logn), &d_tw);
       if (rc) return rc;
     }
-    if (ClusterPlan::wanted(logn)) {
-      rc = cluster.init(logn);
-      if (rc) return rc;
-    }
-    if (SmPlan::wanted(logn)) {
+    if (logn == SmGeom::LOGN && opt.fft_sm_min_batch > 0) {
+      sm.min_batch = opt.fft_sm_min_batch;
       rc = sm.init(dev);
       if (rc) return rc;
     }
@@ -651,7 +604,6 @@ struct FftPlanCore {
     if (d_hw) cudaFree(d_hw);
     if (d_buf) cudaFree(d_buf);
     large.destroy();
-    cluster.destroy();
     sm.destroy();
     if (stream) cudaStreamDestroy(stream);
     sg_in.release();
@@ -659,18 +611,14 @@ struct FftPlanCore {
   }
   int run_c2c(const float2 *in, float2 *out, int batch, cudaStream_t st) {
     const float scale = fwd ? 1.0f / (float)N : 1.0f;
-    if (cluster.ok())
-      return fwd ? cluster.run<false, false>(in, out, nullptr, batch, scale, st)
-                 : cluster.run<true, false>(in, out, nullptr, batch, scale, st);
-    if (sm.ok())
+    if (sm.use_for(batch))
       return fwd ? sm.run<false, kSmComplex>(in, out, nullptr, batch, scale, st)
                  : sm.run<true, kSmComplex>(in, out, nullptr, batch, scale, st);
     if (is_large()) return large.run_c2c(!fwd, in, out, batch, scale, st);
     return launch_cfft(logn, !fwd, in, out, d_tw, batch, scale, st);
   }
   int run_real(const float2 *in, float2 *out, int batch, cudaStream_t st) {
-    if (cluster.ok() && fwd) return cluster.run<false, true>(in, out, d_w2, batch, fwd_scale(), st);
-    if (sm.ok())
+    if (sm.use_for(batch))
       return fwd ? sm.run<false, kSmRealFwd>(in, out, d_hw, batch, fwd_scale(), st)
                  : sm.run<true, kSmRealInv>(in, out, d_hw, batch, 1.0f, st);
     if (is_large()) return large.run_real(!fwd, in, out, d_w2, d_hw, batch, fwd_scale(), st);
@@ -724,7 +672,7 @@ extern "C" int b2f_cfft_exec_host(b2f_cfft *plan, float *cdata, int batch) {
   int rc = c.ensure_buf();
   if (rc) return rc;
   const size_t bytes = (size_t)batch * c.N * sizeof(float2);
-  if (bytes <= zerocopy_max()) {
+  if (bytes <= (size_t)c.opt.zerocopy_max) {
     if ((rc = c.sg_in.ensure(bytes)) || (rc = c.sg_out.ensure(bytes))) return rc;
     memcpy(c.sg_in.pin, cdata, bytes);
     if ((rc = c.run_c2c((const float2 *)c.sg_in.pin, (float2 *)c.sg_out.pin, batch, c.stream))) return rc;
@@ -778,7 +726,7 @@ extern "C" int b2f_rfft_exec_host(b2f_rfft *plan, float *cdata, float *r, int ba
   const size_t bytes = (size_t)batch * c.N * sizeof(float2);
   // forward reads the reals (cl_fft.cpp:273-275), inverse reads the spectrum (284)
   const void *src = c.fwd ? (const void *)r : (const void *)cdata;
-  if (bytes <= zerocopy_max()) {
+  if (bytes <= (size_t)c.opt.zerocopy_max) {
     if ((rc = c.sg_in.ensure(bytes)) || (rc = c.sg_out.ensure(bytes))) return rc;
     memcpy(c.sg_in.pin, src, bytes);
     if ((rc = c.run_real((const float2 *)c.sg_in.pin, (float2 *)c.sg_out.pin, batch, c.stream))) return rc;
@@ -805,16 +753,23 @@ struct b2f_pconv {
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second half of the channels in the pipelined host call
   Staging sg_in, sg_in2, sg_out;
   int cluster = 1;
-  // general path (pts > 2^kPconvMaxLogP): batched real-FFT plans + pad / MAC / overlap-add kernels
+  Options opt;
+  int failed = 0;           // sticky: a multi-stream host call broke off half way, the state is not trustworthy
+  // general path (pts > 2^kPconvMaxLogP): batched real-FFT plans + pad / MAC / overlap-add kernels; ring positions in
+  // device memory (d_state), one CUDA graph per block kind for the host call
   FftPlanCore *gfwd = nullptr, *ginv = nullptr;
   float *d_pad = nullptr;   // [channels][2*pts]
   float2 *d_Y = nullptr;    // [channels][pts]
+  int *d_state = nullptr;   // {wp, wp2}
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [time-varying]: H2D, the block's launches, D2H on fixed buffers
   bool general() const { return gfwd != nullptr; }
   size_t ring_elems() const { return (size_t)channels * nparts * pts; }
   void destroy() {
     DeviceGuard guard(device);  // a failed create may carry an invalid ordinal: the guard swallows that
+    for (cudaGraphExec_t g : graph)
+      if (g) cudaGraphExecDestroy(g);
     for (void *p : {(void *)d_fdl, (void *)d_irs, (void *)d_tw, (void *)d_w2, (void *)d_tail, (void *)d_in1,
-                    (void *)d_in2, (void *)d_out, (void *)d_ir, (void *)d_pad, (void *)d_Y})
+                    (void *)d_in2, (void *)d_out, (void *)d_ir, (void *)d_pad, (void *)d_Y, (void *)d_state})
       if (p) cudaFree(p);
     for (FftPlanCore *p : {gfwd, ginv})
       if (p) {
@@ -860,13 +815,12 @@ static int launch_pconv_step_tt(const PconvArgs &a, int channels, int S, cudaStr
   return B2F_OK;
 }
 template <int LOGP, bool TV>
-static int launch_pconv_step_t(const PconvArgs &a, int channels, int S, cudaStream_t st) {
+static int launch_pconv_step_t(const PconvArgs &a, int channels, int S, int tma_opt, cudaStream_t st) {
   // Which MAC feeds the fused kernel: registers (128-bit loads, 16 in flight per thread) or the TMA ring. Measured on
   // B200 (256 channels x 480000 taps, TB/s, registers vs TMA): pts 512 7.28 vs 6.88; pts 1024 6.36 vs 6.03 (registers
   // since the MAC walks each partition's whole frame at once); pts 2048 4.65 vs 6.07; pts 4096 4.09 vs 3.86 (4.43 at
-  // 1024 channels, where TMA wins). B2F_PCONV_TMA=0|1 forces one or the other.
-  const char *force = getenv("B2F_PCONV_TMA");
-  const bool use_tma = force ? (force[0] == '1') : ((LOGP == 11 && channels >= 64) || (LOGP == 12 && channels >= 512));
+  // 1024 channels, where TMA wins). Option pconv_tma = 0 | 1 forces one or the other.
+  const bool use_tma = tma_opt >= 0 ? tma_opt == 1 : ((LOGP == 11 && channels >= 64) || (LOGP == 12 && channels >= 512));
   return use_tma ? launch_pconv_step_tt<LOGP, TV, true>(a, channels, S, st)
                  : launch_pconv_step_tt<LOGP, TV, false>(a, channels, S, st);
 }
@@ -899,13 +853,13 @@ static int launch_pconv_push_t(const float *ir, size_t stride, b2f_pconv *h, cud
     default: return B2F_ERR_UNSUPPORTED; \
   }
 
-static int launch_pconv_step(int logp, bool tv, const PconvArgs &a, int channels, int S, cudaStream_t st) {
+static int launch_pconv_step(int logp, bool tv, const PconvArgs &a, int channels, int S, int tma_opt, cudaStream_t st) {
   if (tv) {
-#define CALL(L) launch_pconv_step_t<L, true>(a, channels, S, st)
+#define CALL(L) launch_pconv_step_t<L, true>(a, channels, S, tma_opt, st)
     B2F_DISPATCH_LOGP(logp, CALL)
 #undef CALL
   } else {
-#define CALL(L) launch_pconv_step_t<L, false>(a, channels, S, st)
+#define CALL(L) launch_pconv_step_t<L, false>(a, channels, S, tma_opt, st)
     B2F_DISPATCH_LOGP(logp, CALL)
 #undef CALL
   }
@@ -928,6 +882,7 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   b2f_pconv *h = new (std::nothrow) b2f_pconv;
   if (!h) return B2F_ERR_ALLOC;
   h->device = device, h->cvs = cvs, h->pts = pts, h->logp = logp, h->channels = channels;
+  h->opt = current_options();
   h->nparts = cvs / pts;  // truncating, cl_conv.cpp:143
   h->wp = 0;
   h->wp2 = h->nparts - 1;
@@ -938,13 +893,17 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   int S = 1;
   while (S < 8 && channels * S < 148 && S * 2 <= h->nparts) S *= 2;
   while (S < 8 && channels * S < 2048 && h->nparts / (2 * S) >= 256) S *= 2;
-  if (const char *e = getenv("B2F_PCONV_CLUSTER")) S = atoi(e);
-  h->cluster = S;
   auto fail = [&](int code) {
     h->destroy();
     delete h;
     return code;
   };
+  if (h->opt.pconv_cluster) {  // forced split: a power of two within the portable cluster size, at most one CTA per partition
+    const long long f = h->opt.pconv_cluster;
+    if ((f != 1 && f != 2 && f != 4 && f != 8) || f > h->nparts) return fail(B2F_ERR_INVALID_VALUE);
+    S = (int)f;
+  }
+  h->cluster = S;
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "stream"));
   if (logp <= kPconvMaxLogP) {
@@ -961,6 +920,12 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
       return fail(cuda_fail(e, "cudaMalloc pad"));
     if ((e = cudaMalloc((void **)&h->d_Y, (size_t)channels * pts * sizeof(float2))) != cudaSuccess)
       return fail(cuda_fail(e, "cudaMalloc Y"));
+    if ((e = cudaMalloc((void **)&h->d_state, 2 * sizeof(int))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc state"));
+    const int st0[2] = {h->wp, h->wp2};
+    if ((e = cudaMemcpy(h->d_state, st0, sizeof(st0), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "state"));
+    // nothing may be allocated while a block's launches are being captured into a graph
+    for (FftPlanCore *pl : {h->gfwd, h->ginv})
+      if (pl->is_large() && (rc = pl->large.ensure_scratch())) return fail(rc);
   }
   const size_t ring = h->ring_elems() * sizeof(float2), blk = (size_t)channels * pts * sizeof(float);
   if ((e = cudaMalloc((void **)&h->d_fdl, ring)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc fdl"));
@@ -987,9 +952,15 @@ extern "C" int b2f_pconv_reset(b2f_pconv *h) {
   B2F_ON_DEVICE(h->device);
   CK(cudaMemsetAsync(h->d_fdl, 0, h->ring_elems() * sizeof(float2), h->stream));
   CK(cudaMemsetAsync(h->d_tail, 0, (size_t)h->channels * h->pts * sizeof(float), h->stream));
-  CK(cudaStreamSynchronize(h->stream));
   h->wp = 0;
   h->wp2 = h->nparts - 1;
+  if (h->d_state) {
+    const int st0[2] = {h->wp, h->wp2};
+    CK(cudaMemcpyAsync(h->d_state, st0, sizeof(st0), cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->stream2) CK(cudaStreamSynchronize(h->stream2));
+  h->failed = 0;
   return B2F_OK;
 }
 
@@ -1015,28 +986,42 @@ static int pconv_general_push(b2f_pconv *h, const float *ir, size_t stride, cuda
   }
   return B2F_OK;
 }
+// R(x) of one block per channel into the ring frame named by the device-side position `which` (0: wp, 1: wp2)
+static int pconv_general_frame_state(b2f_pconv *h, const float *x, float2 *ring, int which, cudaStream_t st) {
+  const int pts = h->pts;
+  dim3 grid((2 * pts + 255) / 256, h->channels, 1);
+  pconv_pad_kernel<<<grid, 256, 0, st>>>(x, (size_t)pts, h->d_pad, pts);
+  CK(cudaGetLastError());
+  int rc = h->gfwd->run_real((const float2 *)h->d_pad, h->d_Y, h->channels, st);
+  if (rc) return rc;
+  dim3 gs((pts / 2 + 255) / 256, h->channels, 1);
+  pconv_ring_store_kernel<<<gs, 256, 0, st>>>(h->d_Y, ring, pts, h->nparts, h->d_state, which);
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
+// One block on the general path. Every launch takes the ring positions from h->d_state, the last one advances
+// them: the sequence is the same for every block, which is what lets the host call replay it as a CUDA graph.
 static int pconv_general_step(b2f_pconv *h, bool tv, float *d_out, const float *d_in1, const float *d_in2, cudaStream_t st) {
   const int pts = h->pts;
-  int rc = pconv_general_frame(h, d_in1, pts, h->d_fdl, h->wp, st);
+  int rc = pconv_general_frame_state(h, d_in1, h->d_fdl, 0, st);
   if (rc) return rc;
-  if (tv && (rc = pconv_general_frame(h, d_in2, pts, h->d_irs, h->wp2, st))) return rc;
-  const int rp = (h->wp + 1 == h->nparts) ? 0 : h->wp + 1;
+  if (tv && (rc = pconv_general_frame_state(h, d_in2, h->d_irs, 1, st))) return rc;
   // TMA-fed MAC by default on this path (measured 3-16 % faster with many channels, 2x for a mono 4M-tap IR);
-  // B2F_PCONV_TMA=0 selects the register-fed kernel.
-  const char *force = getenv("B2F_PCONV_TMA");
-  const bool use_tma = !(force && force[0] == '0');
-  if (use_tma) {
+  // option pconv_tma = 0 selects the register-fed kernel.
+  if (h->opt.pconv_tma != 0) {
     if ((rc = set_smem(pconv_mac_tma_kernel, kMacTmaSmem))) return rc;
     dim3 gt(pts / kMacTileBins, h->channels, 1);
-    pconv_mac_tma_kernel<<<gt, 288, kMacTmaSmem, st>>>(h->d_fdl, h->d_irs, h->d_Y, pts, h->nparts, rp);
+    pconv_mac_tma_kernel<<<gt, 288, kMacTmaSmem, st>>>(h->d_fdl, h->d_irs, h->d_Y, pts, h->nparts, h->d_state);
   } else {
     dim3 gm((pts / 2 + 255) / 256, h->channels, 1);
-    pconv_mac_kernel<<<gm, 256, 0, st>>>(h->d_fdl, h->d_irs, h->d_Y, pts, h->nparts, rp);
+    pconv_mac_kernel<<<gm, 256, 0, st>>>(h->d_fdl, h->d_irs, h->d_Y, pts, h->nparts, h->d_state);
   }
   CK(cudaGetLastError());
   if ((rc = h->ginv->run_real(h->d_Y, h->d_Y, h->channels, st))) return rc;
   dim3 go((pts + 255) / 256, h->channels, 1);
   pconv_ola_kernel<<<go, 256, 0, st>>>((const float *)h->d_Y, h->d_tail, d_out, pts);
+  CK(cudaGetLastError());
+  pconv_advance_kernel<<<1, 32, 0, st>>>(h->d_state, h->nparts, tv ? 1 : 0);
   CK(cudaGetLastError());
   return B2F_OK;
 }
@@ -1053,13 +1038,18 @@ extern "C" int b2f_pconv_push_ir_host(b2f_pconv *h, const float *ir, size_t ir_s
   if (!h || !ir || ir_stride < (size_t)h->nparts * h->pts) return B2F_ERR_INVALID_VALUE;
   B2F_ON_DEVICE(h->device);
   const size_t per = (size_t)h->nparts * h->pts;
-  if (!h->d_ir) CK(cudaMalloc((void **)&h->d_ir, (size_t)h->channels * per * sizeof(float)));
-  CK(cudaMemcpy2DAsync(h->d_ir, per * sizeof(float), ir, ir_stride * sizeof(float), per * sizeof(float), h->channels,
-                       cudaMemcpyHostToDevice, h->stream));
-  int rc = h->general() ? pconv_general_push(h, h->d_ir, per, h->stream) : launch_pconv_push(h->logp, h->d_ir, per, h, h->stream);
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(h->stream));
-  return B2F_OK;
+  // the time-domain IRs are needed on the device only for the duration of this call (1.96 GB at 1024 x 937 x 512)
+  CK(cudaMalloc((void **)&h->d_ir, (size_t)h->channels * per * sizeof(float)));
+  int rc = B2F_OK;
+  cudaError_t e = cudaMemcpy2DAsync(h->d_ir, per * sizeof(float), ir, ir_stride * sizeof(float), per * sizeof(float),
+                                    h->channels, cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy2DAsync ir");
+  if (!rc) rc = h->general() ? pconv_general_push(h, h->d_ir, per, h->stream) : launch_pconv_push(h->logp, h->d_ir, per, h, h->stream);
+  e = cudaStreamSynchronize(h->stream);
+  if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+  cudaFree(h->d_ir);
+  h->d_ir = nullptr;
+  return rc;
 }
 
 static int pconv_enqueue(b2f_pconv *h, bool tv, float *d_out, const float *d_in1, const float *d_in2, cudaStream_t st) {
@@ -1069,7 +1059,7 @@ static int pconv_enqueue(b2f_pconv *h, bool tv, float *d_out, const float *d_in1
   a.tw = h->d_tw, a.w2 = h->d_w2;
   a.nparts = h->nparts, a.wp = h->wp, a.wp2 = h->wp2;
   int rc = h->general() ? pconv_general_step(h, tv, d_out, d_in1, d_in2, st)
-                        : launch_pconv_step(h->logp, tv, a, h->channels, h->cluster, st);
+                        : launch_pconv_step(h->logp, tv, a, h->channels, h->cluster, (int)h->opt.pconv_tma, st);
   if (rc) return rc;
   h->wp = h->wp != h->nparts - 1 ? h->wp + 1 : 0;             // cl_conv.cpp:424
   if (tv) h->wp2 = h->wp2 == 0 ? h->nparts - 1 : h->wp2 - 1;  // cl_conv.cpp:519
@@ -1083,18 +1073,22 @@ static int pconv_launch_range(b2f_pconv *h, float *d_out, const float *d_in, int
   a.in1 = d_in + blk, a.in2 = nullptr, a.out = d_out + blk;
   a.tw = h->d_tw, a.w2 = h->d_w2;
   a.nparts = h->nparts, a.wp = h->wp, a.wp2 = h->wp2;
-  return launch_pconv_step(h->logp, false, a, n, h->cluster, st);
+  return launch_pconv_step(h->logp, false, a, n, h->cluster, (int)h->opt.pconv_tma, st);
 }
 extern "C" int b2f_pconv_process_dev(b2f_pconv *h, void *d_out, const void *d_in, void *stream) {
   if (!h || !d_out || !d_in || !al16(d_out) || !al16(d_in)) return B2F_ERR_INVALID_VALUE;
+  if (h->failed) return h->failed;
   B2F_ON_DEVICE(h->device);
   return pconv_enqueue(h, false, (float *)d_out, (const float *)d_in, nullptr, (cudaStream_t)stream);
 }
 extern "C" int b2f_pconv_process_tv_dev(b2f_pconv *h, void *d_out, const void *d_in1, const void *d_in2, void *stream) {
   if (!h || !d_out || !d_in1 || !d_in2 || !al16(d_out) || !al16(d_in1) || !al16(d_in2)) return B2F_ERR_INVALID_VALUE;
+  if (h->failed) return h->failed;
   B2F_ON_DEVICE(h->device);
   return pconv_enqueue(h, true, (float *)d_out, (const float *)d_in1, (const float *)d_in2, (cudaStream_t)stream);
 }
+// device buffers behind the host entry points, allocated by the first call that does not run on the pinned
+// buffers directly
 static int pconv_host_bufs(b2f_pconv *h, bool tv) {
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
   if (!h->d_in1) CK(cudaMalloc((void **)&h->d_in1, blk));
@@ -1102,13 +1096,47 @@ static int pconv_host_bufs(b2f_pconv *h, bool tv) {
   if (tv && !h->d_in2) CK(cudaMalloc((void **)&h->d_in2, blk));
   return B2F_OK;
 }
+// General path (7-9 launches per block): the host call replays H2D + launches + D2H as ONE CUDA graph, captured
+// from the very code the device entry points run (pconv_general_step) on the handle's fixed buffers. The ring
+// positions are device-resident, so no node parameter changes between blocks. Blocks above the bounce limit (the
+// throughput regime) and option graph = 0 take the plain stream path.
+static int pconv_graph_call(b2f_pconv *h, bool tv, float *out, const float *in1, const float *in2) {
+  const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
+  int rc;
+  if ((rc = pconv_host_bufs(h, tv))) return rc;
+  if ((rc = h->sg_in.ensure(blk)) || (rc = h->sg_out.ensure(blk)) || (tv && (rc = h->sg_in2.ensure(blk)))) return rc;
+  cudaGraphExec_t &ge = h->graph[tv ? 1 : 0];
+  if (!ge) {
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    cudaError_t e = cudaMemcpyAsync(h->d_in1, h->sg_in.pin, blk, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && tv) e = cudaMemcpyAsync(h->d_in2, h->sg_in2.pin, blk, cudaMemcpyHostToDevice, h->stream);
+    rc = e == cudaSuccess ? pconv_general_step(h, tv, h->d_out, h->d_in1, h->d_in2, h->stream) : cuda_fail(e, "capture H2D");
+    if (!rc && (e = cudaMemcpyAsync(h->sg_out.pin, h->d_out, blk, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+      rc = cuda_fail(e, "capture D2H");
+    e = cudaStreamEndCapture(h->stream, &g);
+    if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamEndCapture");
+    if (!rc && (e = cudaGraphInstantiate(&ge, g, 0)) != cudaSuccess) rc = cuda_fail(e, "cudaGraphInstantiate");
+    if (g) cudaGraphDestroy(g);
+    if (rc) return rc;
+  }
+  memcpy(h->sg_in.pin, in1, blk);
+  if (tv) memcpy(h->sg_in2.pin, in2, blk);
+  CK(cudaGraphLaunch(ge, h->stream));
+  h->wp = h->wp != h->nparts - 1 ? h->wp + 1 : 0;             // host mirror of d_state
+  if (tv) h->wp2 = h->wp2 == 0 ? h->nparts - 1 : h->wp2 - 1;
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(out, h->sg_out.pin, blk);
+  return B2F_OK;
+}
 extern "C" int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in) {
   if (!h || !out || !in) return B2F_ERR_INVALID_VALUE;
+  if (h->failed) return h->failed;
   B2F_ON_DEVICE(h->device);
-  int rc = pconv_host_bufs(h, false);
-  if (rc) return rc;
+  int rc;
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
-  if (blk <= zerocopy_max()) {
+  if (h->general() && h->opt.graph && blk <= kBounceMax) return pconv_graph_call(h, false, out, in, nullptr);
+  if (blk <= (size_t)h->opt.zerocopy_max) {
     if ((rc = h->sg_in.ensure(blk)) || (rc = h->sg_out.ensure(blk))) return rc;
     memcpy(h->sg_in.pin, in, blk);
     if ((rc = pconv_enqueue(h, false, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, nullptr, h->stream))) return rc;
@@ -1116,22 +1144,36 @@ extern "C" int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in)
     memcpy(out, h->sg_out.pin, blk);
     return B2F_OK;
   }
+  if ((rc = pconv_host_bufs(h, false))) return rc;
   // Many channels, blocks too large for the bounce buffer (the copies go straight from / to the caller's memory,
   // asynchronously when it is pinned): the two halves of the channels run on two streams, so that the second
   // half's upload overlaps the first half's kernel and the first half's download the second half's kernel.
-  if (!h->general() && h->channels >= 128 && blk > kBounceMax && !getenv("B2F_PCONV_NO_PIPELINE")) {
+  if (!h->general() && h->channels >= 128 && blk > kBounceMax && h->opt.pconv_pipeline) {
     if (!h->stream2) CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     const int n0 = h->channels / 2, n1 = h->channels - n0;
     const size_t b0 = (size_t)n0 * h->pts, bytes0 = b0 * sizeof(float), bytes1 = (size_t)n1 * h->pts * sizeof(float);
-    CK(cudaMemcpyAsync(h->d_in1, in, bytes0, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_in1 + b0, in + b0, bytes1, cudaMemcpyHostToDevice, h->stream2));
-    if ((rc = pconv_launch_range(h, h->d_out, h->d_in1, 0, n0, h->stream))) return rc;
-    if ((rc = pconv_launch_range(h, h->d_out, h->d_in1, n0, n1, h->stream2))) return rc;
-    CK(cudaMemcpyAsync(out, h->d_out, bytes0, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(out + b0, h->d_out + b0, bytes1, cudaMemcpyDeviceToHost, h->stream2));
+    // Every channel's frame `wp` and overlap tail are rewritten by this block: if anything fails after the first
+    // enqueue, both streams are drained (the caller's buffers must not be touched after we return) and the handle
+    // is marked failed -- half its channels would be one block ahead of the other half -- until b2f_pconv_reset().
+    auto run = [&]() -> int {
+      int r;
+      CK(cudaMemcpyAsync(h->d_in1, in, bytes0, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->d_in1 + b0, in + b0, bytes1, cudaMemcpyHostToDevice, h->stream2));
+      if ((r = pconv_launch_range(h, h->d_out, h->d_in1, 0, n0, h->stream))) return r;
+      if ((r = pconv_launch_range(h, h->d_out, h->d_in1, n0, n1, h->stream2))) return r;
+      CK(cudaMemcpyAsync(out, h->d_out, bytes0, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(out + b0, h->d_out + b0, bytes1, cudaMemcpyDeviceToHost, h->stream2));
+      return B2F_OK;
+    };
+    rc = run();
+    const cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->stream2);
+    if (!rc && e1 != cudaSuccess) rc = cuda_fail(e1, "cudaStreamSynchronize");
+    if (!rc && e2 != cudaSuccess) rc = cuda_fail(e2, "cudaStreamSynchronize");
+    if (rc) {
+      h->failed = rc;
+      return rc;
+    }
     h->wp = h->wp != h->nparts - 1 ? h->wp + 1 : 0;  // cl_conv.cpp:424
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaStreamSynchronize(h->stream2));
     return B2F_OK;
   }
   if ((rc = h2d(h->d_in1, in, blk, h->sg_in, h->stream))) return rc;
@@ -1140,11 +1182,12 @@ extern "C" int b2f_pconv_process_host(b2f_pconv *h, float *out, const float *in)
 }
 extern "C" int b2f_pconv_process_tv_host(b2f_pconv *h, float *out, const float *in1, const float *in2) {
   if (!h || !out || !in1 || !in2) return B2F_ERR_INVALID_VALUE;
+  if (h->failed) return h->failed;
   B2F_ON_DEVICE(h->device);
-  int rc = pconv_host_bufs(h, true);
-  if (rc) return rc;
+  int rc;
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
-  if (blk <= zerocopy_max()) {
+  if (h->general() && h->opt.graph && blk <= kBounceMax) return pconv_graph_call(h, true, out, in1, in2);
+  if (blk <= (size_t)h->opt.zerocopy_max) {
     if ((rc = h->sg_in.ensure(blk)) || (rc = h->sg_in2.ensure(blk)) || (rc = h->sg_out.ensure(blk))) return rc;
     memcpy(h->sg_in.pin, in1, blk);
     memcpy(h->sg_in2.pin, in2, blk);
@@ -1155,6 +1198,7 @@ extern "C" int b2f_pconv_process_tv_host(b2f_pconv *h, float *out, const float *
     memcpy(out, h->sg_out.pin, blk);
     return B2F_OK;
   }
+  if ((rc = pconv_host_bufs(h, true))) return rc;
   if ((rc = h2d(h->d_in1, in1, blk, h->sg_in, h->stream))) return rc;
   if ((rc = h2d(h->d_in2, in2, blk, h->sg_in2, h->stream))) return rc;
   if ((rc = pconv_enqueue(h, true, h->d_out, h->d_in1, h->d_in2, h->stream))) return rc;
@@ -1181,6 +1225,7 @@ struct b2f_dconv {
   float *d_coefs = nullptr, *d_grev = nullptr, *d_in1 = nullptr, *d_in2 = nullptr, *d_out = nullptr;
   cudaStream_t stream = nullptr;
   Staging sg_in, sg_in2, sg_out;
+  Options opt;
   int L() const { return irsize + vsize; }
   void destroy() {
     DeviceGuard guard(device);  // a failed create may carry an invalid ordinal: the guard swallows that
@@ -1206,6 +1251,7 @@ extern "C" int b2f_dconv_create(b2f_dconv **out, int device, int irsize, int vsi
   if (!h) return B2F_ERR_ALLOC;
   h->device = device, h->irsize = irsize, h->vsize = vsize, h->channels = channels;
   h->max_blocks = max_blocks < 1 ? 1 : max_blocks;
+  h->opt = current_options();
   auto fail = [&](int code) {
     h->destroy();
     delete h;
@@ -1336,7 +1382,7 @@ extern "C" int b2f_dconv_process_host(b2f_dconv *h, float *out, const float *in,
   int rc = dconv_host_bufs(h, false);
   if (rc) return rc;
   const size_t bytes = (size_t)h->channels * nblocks * h->vsize * sizeof(float);
-  if (bytes <= zerocopy_max()) {
+  if (bytes <= (size_t)h->opt.zerocopy_max) {
     if ((rc = h->sg_in.ensure(bytes)) || (rc = h->sg_out.ensure(bytes))) return rc;
     memcpy(h->sg_in.pin, in, bytes);
     if ((rc = dconv_enqueue(h, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, nblocks, h->stream))) return rc;
@@ -1354,7 +1400,7 @@ extern "C" int b2f_dconv_process_tv_host(b2f_dconv *h, float *out, const float *
   int rc = dconv_host_bufs(h, true);
   if (rc) return rc;
   const size_t bytes = (size_t)h->channels * h->vsize * sizeof(float);
-  if (bytes <= zerocopy_max()) {
+  if (bytes <= (size_t)h->opt.zerocopy_max) {
     if ((rc = h->sg_in.ensure(bytes)) || (rc = h->sg_in2.ensure(bytes)) || (rc = h->sg_out.ensure(bytes))) return rc;
     memcpy(h->sg_in.pin, in1, bytes);
     memcpy(h->sg_in2.pin, in2, bytes);

@@ -1,5 +1,7 @@
-// fft_large.cuh -- transforms too long for one CTA's shared memory (N = 2^15, 2^16 complex, i.e. the
-// 65536- and 131072-point real FFTs of BASELINE config 5), as a four-step factorisation N = N1 * N2:
+// fft_large.cuh -- transforms too long for one CTA's shared memory as a four-step factorisation N = N1 * N2, two
+// launches with a scratch matrix in between. Used for N = 2^16 complex (131072-point real) at any batch and for
+// N = 2^15 (the 65536-point real FFT of BASELINE config 5) at SMALL batches, where spreading one transform over the
+// whole GPU beats the one-SM kernel of fft_sm.cuh (which takes over from ~100 transforms per call):
 //
 //   columns kernel: for every column n2, an N1-point FFT over n1 of x[N2*n1 + n2], times W_N^(n2*k1),
 //                   written to a scratch matrix T[k1][n2]. A CTA owns C adjacent columns (128-byte
@@ -13,8 +15,10 @@
 // (cl_fft.cpp:138-151), which at N = 32768 re-read and re-write the whole array 16 times.
 // HBM traffic here: one read + one write per step; the scratch matrix is written by step 1 and read by
 // step 2 back to back, so it is served from the 126 MB L2 when the batch chunk fits.
-//
-// The real-FFT split/unsplit (cl_fft.cpp:178-205) runs as a separate element-wise pass for now.
+// The real-FFT split (cl_fft.cpp:178-191) is fused into the rows kernel, the unsplit (192-205) into a columns kernel
+// with mirrored column ownership; rfft_split_kernel is the unfused pass kept behind option separate_split.
+// Two single-launch variants built in round 1 (4-CTA clusters with a DSMEM transposition; 8-CTA clusters with an
+// L2-resident scratch) lost to this pair and were removed; profiles/r01_fft_cluster_notes.md has their numbers.
 #pragma once
 
 #include "fft_core.cuh"
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(256, 2)
 // members of every pair (i, N-i) = ((k1,k2), (N1-k1, N2-1-k2)) sit in its shared memory; every pair is
 // evaluated once (folded table hw, scale included) and both members are stored, in 64-byte runs.
 // One row group g of one transform: scratch_b / out_b point at the transform's scratch matrix / output.
-// CG: read the scratch with ld.global.cg (it was written by other CTAs of the cluster in this very launch).
+// CG: read the scratch with ld.global.cg.
 struct NoHook {
   __device__ __forceinline__ void operator()() const {}
 };
@@ -354,153 +358,6 @@ __global__ void __launch_bounds__(RowsGeom<LOG1, LOG2, RBT>::THREADS, LARGE_ROWS
         scratch + (size_t)b * N, out + (size_t)b * N, smem, tw2, hw, scale, blockIdx.x, hook, xin);
     __syncthreads();
   }
-}
-
-// ---- both steps in ONE launch: an 8-CTA thread-block cluster per transform, scratch private to the cluster ---------
-// CTA r of a cluster is column group r in the first step and row group r in the second (N2/C == N1/RB == 8 for
-// N = 2^15). The scratch matrix belongs to the cluster -- three buffers of N complex values, reused for every
-// transform the cluster works through -- so the ~28 MB of scratch of a whole grid stays resident in the 126 MB
-// L2 and HBM sees the algorithmic bytes only (the two-launch path moves every transform through HBM twice).
-//
-// Software pipeline of one CTA (k = iteration, b_k = the cluster's k-th transform):
-//   cp.async prefetch of the columns of b_{k+2} into a shared-memory stage   (HBM latency off the critical path)
-//   columns of b_{k+1}: stage -> N1-point FFTs -> twiddle -> scratch[(k+1) % 3]
-//   wait(k)      "every column group of b_k is in the scratch"; signalled before the step above, so the skew
-//                between the 8 CTAs and the store drain hide behind it
-//   rows of b_k: scratch[k % 3] (ld.global.cg, L2) -> N2-point FFTs -> signal(k+1) -> [split] -> out
-// Three buffers: the columns of b_{k+1} are written while a slower CTA of the cluster may still read the rows of
-// b_{k-1}; it cannot be further behind, because this CTA passed wait(k-1), i.e. everybody finished rows b_{k-2}.
-template <int LOG1, int LOG2>
-struct FusedGeom {
-  using L = LargeGeom<LOG1, LOG2>;
-  static constexpr int WORK_F2 = (L::SMEM_A > L::SMEM_B ? L::SMEM_A : L::SMEM_B) / (int)sizeof(float2);
-  static constexpr int WORK_F2_AL = (WORK_F2 + 1) & ~1;            // 16-byte aligned stage behind it
-  static constexpr int STAGE_F2 = L::N1 * L::C;                     // [N1][C] float2
-  static constexpr int TW1_F2 = sched_tw_total(L::G1::S) + 1, TW2_F2 = sched_tw_total(L::G2::S) + 1;  // pass twiddles
-  static constexpr int SMEM_BYTES = (WORK_F2_AL + STAGE_F2 + TW1_F2 + TW2_F2) * (int)sizeof(float2);
-  static constexpr int NBUF = 3;
-};
-
-// MINB: resident CTAs per SM the register budget is set for. 2: all E inter-step twiddles of a thread stay in
-// registers for the whole launch (128 registers). 3: only 4 + 3 of them do -- the thread's rows are k1 = t + 32a + 8b,
-// so W^(n2 k1) = W^(n2 (t + 32a)) * W^(n2 8b), both factors exact table entries, one extra rounding -- which fits
-// 85 registers: 24 warps per SM instead of 16 hide more of the instruction and barrier latency of the two steps.
-template <int LOG1, int LOG2, bool INV, bool REAL, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-    large_fused_kernel(const float2 *in, float2 *out, float2 *scratch, const float2 *__restrict__ tw1,
-                       const float2 *__restrict__ tw2, const float2 *__restrict__ twl,
-                       const float2 *__restrict__ hw, int batch, float scale) {
-  using L = LargeGeom<LOG1, LOG2>;
-  using F = FusedGeom<LOG1, LOG2>;
-  constexpr int N1 = L::N1, N2 = L::N2, N = L::N, C = L::C, E = L::G1::E, S = 8;
-  static_assert(L::N2 / L::C == S && L::N1 / L::RB == S, "one column group and one row group per CTA of the cluster");
-  static_assert(C % 2 == 0 && (N1 * C / 2) % 256 == 0, "16-byte cp.async chunks, whole rounds of 256 threads");
-  extern __shared__ __align__(16) float2 smem[];
-  float2 *stage = smem + F::WORK_F2_AL;
-  // the two plans' pass twiddles (3 KB) live in shared memory: with 2-3 CTAs of this size per SM the L1 that is
-  // left is too small to keep them resident next to the streaming traffic
-  float2 *stw1 = stage + F::STAGE_F2, *stw2 = stw1 + F::TW1_F2;
-  for (int i = threadIdx.x; i < F::TW1_F2 - 1; i += 256) stw1[i] = __ldg(&tw1[i]);
-  for (int i = threadIdx.x; i < F::TW2_F2 - 1; i += 256) stw2[i] = __ldg(&tw2[i]);
-  const int rank = blockIdx.x % S, cid = blockIdx.x / S, ncl = gridDim.x / S;
-  const int c = threadIdx.x % C, t = threadIdx.x / C;
-  const int n2 = rank * C + c;
-  float2 *smc = smem + c * L::G1::SMEM;
-  if (cid >= batch) return;  // whole cluster
-  constexpr bool FACTORED = MINB >= 3;
-  static_assert(!FACTORED || (LOG1 == 7 && E == 16), "factored twiddles assume rows k1 = t + 8 r, r = 4a + b");
-  float2 wreg[FACTORED ? 4 : E], gpow[4];
-  if constexpr (FACTORED) {
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-      wreg[a] = __ldg(&twl[(size_t)(t + 32 * a) * N2 + n2]);
-      gpow[a] = __ldg(&twl[(size_t)(8 * a) * N2 + n2]);
-      if (INV) wreg[a].y = -wreg[a].y, gpow[a].y = -gpow[a].y;
-    }
-  } else {
-    large_cols_twiddles<LOG1, LOG2, INV>(wreg, twl, n2, t);
-  }
-  float2 *scr = scratch + (size_t)cid * F::NBUF * N;
-
-  // columns [rank*C, rank*C + C) of transform b -> stage[n1][c], 16 bytes (two columns) per cp.async
-  auto prefetch = [&](int b) {
-    const float2 *src = in + (size_t)b * N + rank * C;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage);
-#pragma unroll
-    for (int q = threadIdx.x; q < N1 * C / 2; q += 256) {
-      const int row = q / (C / 2), c2 = q % (C / 2);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)(row * C + 2 * c2) * 8u),
-                   "l"(src + (size_t)row * N2 + 2 * c2)
-                   : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  auto cols = [&](int buf) {
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();  // everybody's part of the stage has landed
-    float2 *dst = scr + (size_t)buf * N + n2;
-    auto load = [&](int idx, int) { return stage[idx * C + c]; };
-    auto store = [&](int idx, float2 v, int slot) {
-      float2 w;
-      if constexpr (FACTORED)
-        w = (slot & 3) ? cmul(wreg[slot >> 2], gpow[slot & 3]) : wreg[slot >> 2];
-      else
-        w = wreg[slot];
-      dst[(size_t)idx * N2] = cmul(v, w);
-    };
-    fft_run<LOG1, INV, false, false, true>(load, store, smc, stw1, t, CtaSync());
-    __syncthreads();  // stage and work buffer are free again
-  };
-
-  // All-to-all barrier of the cluster on shared-memory mbarriers (two, alternating by iteration): after a CTA
-  // barrier, 8 lanes of warp 0 arrive (release.cluster) on the current mbarrier of the 8 CTAs; everybody waits on
-  // its own. Unlike barrier.cluster.arrive/wait -- MEMBAR.ALL.GPU in every warp, CCTL.IVALL (L1 invalidation,
-  // twiddle tables included) after every wait -- one warp fences and no cache is invalidated; the scratch is
-  // read with ld.global.cg, which does not look in L1.
-  __shared__ __align__(8) unsigned long long xbar[2];
-  const uint32_t xb0 = tma::smem_u32(&xbar[0]);
-  if (threadIdx.x == 0) {
-    tma::mbar_init(xb0, S);
-    tma::mbar_init(xb0 + 8, S);
-    tma::fence_barrier_init();
-  }
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  int bars = 0;  // barriers signalled so far; barrier j lives on xbar[j & 1], phase parity (j >> 1) & 1
-  auto signal = [&]() {  // caller has just passed a __syncthreads() after the work being published
-    if (threadIdx.x < S) tma::mbar_arrive_cluster_release(tma::map_to_rank(xb0 + 8 * (bars & 1), threadIdx.x));
-    bars++;
-  };
-  auto wait_for = [&](int j) { tma::mbar_wait(xb0 + 8 * (j & 1), (j >> 1) & 1); };
-
-  int b = cid, nb = cid + ncl, k = 0, j = 0;
-  prefetch(b);
-  cols(0);
-  if (nb < batch) prefetch(nb);
-  signal();
-  while (true) {
-    const bool more = nb < batch;
-    const int kn = (k + 1 == F::NBUF) ? 0 : k + 1;
-    if (more) {
-      cols(kn);
-      if (nb + ncl < batch) prefetch(nb + ncl);
-    }
-    wait_for(j);
-    // barrier j+1 = "my columns of b_{k+1} are in the scratch and I have consumed the rows of b_k": signalled
-    // from inside the rows step, before its stores to `out`, so that the release does not wait for those
-    auto hook = [&]() {
-      if (more) signal();
-    };
-    large_rows_body<LOG1, LOG2, INV, REAL, true, decltype(hook), true>(scr + (size_t)k * N, out + (size_t)b * N, smem,
-                                                                       stw2, hw, scale, rank, hook);
-    __syncthreads();
-    if (!more) break;
-    b = nb;
-    nb += ncl;
-    k = kn;
-    j++;
-  }
-  // nobody leaves while a sibling may still arrive on its mbarriers
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // element-wise real-FFT split (forward, after the complex transform) / unsplit (inverse, before it)

@@ -526,6 +526,32 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::FT)
 // MAC -> inverse rFFT -> overlap-add; the MAC still moves all but a few percent of the bytes.
 // =====================================================================================================
 
+// The ring positions of the general path live in device memory -- state[0] = wp (frame the next input block is
+// written to, cl_conv.cpp:144,424), state[1] = wp2 (frame the next time-varying IR block is written to, 385,519) --
+// so that a block's launch sequence has no host-side parameter that changes from block to block and can be replayed
+// as ONE CUDA graph (the host keeps a mirror for push_ir and the white-box reads).
+// frame the MAC starts reading at: the reference increments wp before convol (cl_conv.cpp:424-429)
+__device__ __forceinline__ int pconv_read_pos(const int *state, int nparts) {
+  const int wp = state[0];
+  return wp + 1 == nparts ? 0 : wp + 1;
+}
+// Y [channels][pts] -> ring frame state[which] of every channel
+__global__ void pconv_ring_store_kernel(const float2 *Y, float2 *ring, int pts, int nparts, const int *state, int which) {
+  const int ch = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  if (i < pts / 2)
+    reinterpret_cast<float4 *>(ring + ((size_t)ch * nparts + state[which]) * pts)[i] =
+        reinterpret_cast<const float4 *>(Y + (size_t)ch * pts)[i];
+}
+// end of a block: wp advances (cl_conv.cpp:424), wp2 retreats when the block was time-varying (519)
+__global__ void pconv_advance_kernel(int *state, int nparts, int tv) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int wp = state[0], wp2 = state[1];
+    state[0] = wp + 1 == nparts ? 0 : wp + 1;
+    if (tv) state[1] = wp2 == 0 ? nparts - 1 : wp2 - 1;
+  }
+}
+
 // in [channels][pts] -> pad [channels][2*pts], upper half zero (cl_conv.cpp:399: half of in1 is written)
 __global__ void pconv_pad_kernel(const float *in, size_t in_stride, float *pad, int pts) {
   const int ch = blockIdx.y;
@@ -536,7 +562,8 @@ __global__ void pconv_pad_kernel(const float *in, size_t in_stride, float *pad, 
 // Y[ch][n] = sum_p FDL[(rp+p) mod nparts][n] (*) IR[p][n], ascending p; bin 0 component-wise
 // (cl_conv_kernels.h:102-118). grid = (pts / 512, channels), 256 threads, two bins per thread.
 __global__ void __launch_bounds__(256)
-    pconv_mac_kernel(const float2 *fdl, const float2 *irs, float2 *Y, int pts, int nparts, int rp) {
+    pconv_mac_kernel(const float2 *fdl, const float2 *irs, float2 *Y, int pts, int nparts, const int *state) {
+  const int rp = pconv_read_pos(state, nparts);
   const int ch = blockIdx.y;
   const int q = blockIdx.x * 256 + threadIdx.x;  // float4 index inside a frame
   const size_t stride4 = pts / 2;
@@ -570,7 +597,8 @@ constexpr int kMacTmaSmem = kMacStages * 2 * kMacSliceBytes + 1024;  // ring + b
 
 // grid = (pts / 512, channels), 288 threads: warps 0-7 consume, warp 8 lane 0 produces.
 __global__ void __launch_bounds__(288)
-    pconv_mac_tma_kernel(const float2 *fdl, const float2 *irs, float2 *Y, int pts, int nparts, int rp) {
+    pconv_mac_tma_kernel(const float2 *fdl, const float2 *irs, float2 *Y, int pts, int nparts, const int *state) {
+  const int rp = pconv_read_pos(state, nparts);
   extern __shared__ __align__(128) unsigned char mac_smem[];
   float4 *ringF = reinterpret_cast<float4 *>(mac_smem);
   float4 *ringG = reinterpret_cast<float4 *>(mac_smem + kMacStages * kMacSliceBytes);

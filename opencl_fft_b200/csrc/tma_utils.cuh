@@ -1,6 +1,6 @@
 // tma_utils.cuh -- inline-PTX helpers for TMA-fed pipelines: 1-D bulk global->shared copies (cp.async.bulk, SASS
 // UBLKCP) whose completion is counted on shared-memory mbarriers. Used by the partitioned-convolution MAC
-// (pconv_kernels.cuh) and by the rows kernel of the large FFT (fft_large.cuh).
+// (pconv_kernels.cuh) and by the one-SM FFT (fft_sm.cuh), whose two input rounds are staged by the TMA engine.
 #pragma once
 
 #include <cstdint>

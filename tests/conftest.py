@@ -53,3 +53,18 @@ def eng():
     if e.device_count() < 1:
         pytest.fail("no CUDA device visible: gpu-marked tests must run on the GPU box")
     return e
+
+
+@pytest.fixture
+def options(eng):
+    """eng.set_option() with the defaults restored afterwards (options are process-wide defaults that a handle
+    copies when it is created; include/b200fft.h lists them)"""
+    saved = {}
+
+    def setter(name, value):
+        saved.setdefault(name, eng.get_option(name))
+        eng.set_option(name, value)
+
+    yield setter
+    for name, value in saved.items():
+        eng.set_option(name, value)

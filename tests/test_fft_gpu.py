@@ -165,21 +165,20 @@ def test_device_pointer_api_matches_host_api(eng):
     assert torch.equal(d2, d_in)
 
 
-@pytest.mark.parametrize("path", ["default", "cluster", "fused", "fused3"])
-@pytest.mark.parametrize("batch", [1, 5, 71, 300])
-def test_large_fft_every_transform_of_a_batch(eng, batch, path, monkeypatch):
-    """The 65536-point real / 32768-point complex transforms: by default two long launches (columns, rows with
-    the real split / unsplit fused); with B2F_CLUSTER_FFT=1 the single-pass kernel on 4-CTA clusters that exchange
-    data through distributed shared memory; with B2F_LARGE_FUSED=1 both steps in one launch on 8-CTA clusters with
-    L2-resident scratch and an mbarrier all-to-all per transform (a persistent cluster loops over several
-    transforms when batch > resident clusters). Check EVERY transform of the batch (a race shows up as a few
-    wrong ones), twice, and that the two runs agree bit for bit."""
-    if path == "cluster":
-        monkeypatch.setenv("B2F_CLUSTER_FFT", "1")  # read when the plan is created
-    if path.startswith("fused"):
-        monkeypatch.setenv("B2F_LARGE_FUSED", "1")
-        if path == "fused3":
-            monkeypatch.setenv("B2F_FUSED_CLUSTERS", "3")  # few clusters: many transforms per cluster, all buffers reused
+@pytest.mark.parametrize("path", ["default", "one_sm", "four_step", "four_step_unfused"])
+@pytest.mark.parametrize("batch", [1, 5, 71, 149, 300])
+def test_large_fft_every_transform_of_a_batch(eng, batch, path, options):
+    """The 65536-point real / 32768-point complex transforms. From ~100 transforms per call: the one-SM kernel
+    (fft_sm.cuh: one pass over HBM, TMA-staged input, rows parked in tensor memory, persistent CTAs looping over the
+    batch -- 149 and 300 make some CTAs take two or three transforms); below: the four-step launch pair
+    (fft_large.cuh). Both are forced for every batch here. Check EVERY transform of the batch (a race shows up as a
+    few wrong ones), twice, and that the two runs agree bit for bit; forward real, inverse real, complex both ways."""
+    if path == "one_sm":
+        options("fft_sm_min_batch", 1)
+    if path.startswith("four_step"):
+        options("fft_sm_min_batch", 0)
+    if path == "four_step_unfused":
+        options("separate_split", 1)
     size = 65536
     rng = np.random.default_rng(batch)
     x = rng.uniform(-1, 1, (batch, size)).astype(np.float32)

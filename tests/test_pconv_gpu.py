@@ -243,13 +243,13 @@ def test_time_varying_multichannel(eng, port):
         assert rel_l2(y[:, k], want) < TOL
 
 
-@pytest.mark.parametrize("tma", ["0", "1"])
+@pytest.mark.parametrize("tma", [0, 1])
 @pytest.mark.parametrize("pts,channels", [(64, 3), (512, 70), (1024, 70), (2048, 2), (8192, 2)])
-def test_both_mac_feeds(eng, port, monkeypatch, tma, pts, channels):
+def test_both_mac_feeds(eng, port, options, tma, pts, channels):
     """The spectral multiply-accumulate exists twice: fed by 128-bit register loads and fed by the TMA engine
-    (cp.async.bulk into an mbarrier ring). The library picks by shape; B2F_PCONV_TMA forces either. Both must
+    (cp.async.bulk into an mbarrier ring). The library picks by shape; option pconv_tma forces either. Both must
     match the oracle, static and time-varying, including ring wrap."""
-    monkeypatch.setenv("B2F_PCONV_TMA", tma)  # read at the first launch of each kernel family
+    options("pconv_tma", tma)  # copied by the handles created below
     nparts = 5
     cvs, nb = nparts * pts, 2 * nparts + 2
     rng = np.random.default_rng(pts + channels)
@@ -269,7 +269,7 @@ def test_both_mac_feeds(eng, port, monkeypatch, tma, pts, channels):
         assert rel_l2(ytv[:, k], np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])) < TOL
 
 
-def test_pipelined_host_call_equals_device_path(eng, monkeypatch):
+def test_pipelined_host_call_equals_device_path(eng, options):
     """Many channels with a block above 1 MB: the synchronous host call runs the two halves of the channels on two
     streams (upload of one half overlapping the kernel of the other). Same bits as the single-stream form and as
     the device-pointer entry point, over enough blocks to wrap the delay line, odd channel count included."""
@@ -286,7 +286,7 @@ def test_pipelined_host_call_equals_device_path(eng, monkeypatch):
         return run_stream(c, x)
 
     y_pipe = host_run()
-    monkeypatch.setenv("B2F_PCONV_NO_PIPELINE", "1")
+    options("pconv_pipeline", 0)
     y_single = host_run()
     assert np.array_equal(y_pipe, y_single)
     c = eng.Clpconv(0, pts * nparts, pts, channels=channels)

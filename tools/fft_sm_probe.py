@@ -1,4 +1,6 @@
-"""A/B of the N = 2^15 paths (B2F_FFT_SM = 0 four-step launch pair, 1 one-SM kernel of fft_sm.cuh): results against float64 for every transform of a batch, then device-resident timing.
+"""A/B of the N = 2^15 paths (mode 0: four-step launch pair, mode 1: one-SM kernel of fft_sm.cuh, selected with the
+fft_sm_min_batch option): results against float64 for every transform of a batch, device-resident timing, and with
+--sweep the small-batch crossover between the two.
 usage: python tools/fft_sm_probe.py [--batch 1024] [--modes 0,1,2]"""
 import argparse
 import json
@@ -17,6 +19,7 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--modes", default="0,1")
 ap.add_argument("--check-batch", type=int, default=300)
 ap.add_argument("--skip-check", action="store_true")
+ap.add_argument("--sweep", action="store_true", help="time r2c at batches 1..592 on both paths")
 ap.add_argument("--kinds", default="r2c,c2c,c2r")
 args = ap.parse_args()
 peak = 6544.7
@@ -54,7 +57,7 @@ total = args.batch * size * 4
 buf = torch.randn(2, total // 4, device="cuda")
 out = torch.empty_like(buf)
 for mode in [int(m) for m in args.modes.split(",")]:
-    os.environ["B2F_FFT_SM"] = str(mode)
+    eng.set_option("fft_sm_min_batch", 1 if mode else 0)
     res = {"mode": mode}
     if not args.skip_check:
         # correctness, every transform, device API
@@ -110,3 +113,19 @@ for mode in [int(m) for m in args.modes.split(",")]:
         res[kind + "_frac"] = round(gbs / peak, 3)
         plan.close()
     print(json.dumps(res), flush=True)
+
+if args.sweep:
+    for b in (1, 8, 32, 64, 96, 128, 148, 222, 296, 444, 592):
+        row = {"batch": b}
+        for mode in (0, 1):
+            eng.set_option("fft_sm_min_batch", 1 if mode else 0)
+            plan = eng.Clrfft(0, size, True, max_batch=b)
+            k = [0]
+
+            def fn():
+                k[0] ^= 1
+                assert plan.transform_dev(buf[k[0]], out[k[0]], b) == 0
+
+            row["four_step_us" if mode == 0 else "one_sm_us"] = round(timeit(fn, 50) * 1e3, 2)
+            plan.close()
+        print(json.dumps(row), flush=True)

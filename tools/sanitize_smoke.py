@@ -27,20 +27,20 @@ for n, batch in ((16, 5), (64, 5), (512, 3), (1024, 3), (4096, 2), (8192, 1)):
     c = np.zeros((batch, n), np.complex64)
     assert eng.Clrfft(0, 2 * n, True, max_batch=batch).transform(c.reshape(-1), r.reshape(-1)) == 0
     assert eng.Clrfft(0, 2 * n, False, max_batch=batch).transform(c.reshape(-1), r.reshape(-1)) == 0
-# large path (two kernels, fused split) and the opt-in cluster kernel
-for env in (None, "1"):
-    if env:
-        os.environ["B2F_CLUSTER_FFT"] = env
+# N = 2^15: the four-step launch pair (small batches) and the one-SM kernel (forced here for a batch of 3)
+for min_batch in (0, 1):
+    eng.set_option("fft_sm_min_batch", min_batch)
     x = crand(3, 32768)
     assert eng.Clcfft(0, 32768, True, max_batch=3).transform(x.reshape(-1)) == 0
+    assert eng.Clcfft(0, 32768, False, max_batch=3).transform(x.reshape(-1)) == 0
     r = rng.uniform(-1, 1, (3, 65536)).astype(np.float32)
     c = np.zeros((3, 32768), np.complex64)
     assert eng.Clrfft(0, 65536, True, max_batch=3).transform(c.reshape(-1), r.reshape(-1)) == 0
     assert eng.Clrfft(0, 65536, False, max_batch=3).transform(c.reshape(-1), r.reshape(-1)) == 0
-os.environ.pop("B2F_CLUSTER_FFT", None)
+eng.set_option("fft_sm_min_batch", 96)
 # partitioned convolution: fused kernel (1 CTA, clusters of 2..8, register- and TMA-fed), general path, time-varying
-for tma in ("0", "1"):
-    os.environ["B2F_PCONV_TMA"] = tma
+for tma in (0, 1):
+    eng.set_option("pconv_tma", tma)
     for pts, nparts, ch in ((64, 5, 1), (512, 9, 3), (512, 5, 200), (1024, 4, 70), (8192, 3, 2)):
         cvs = pts * nparts
         c = eng.Clpconv(0, cvs, pts, channels=ch)
@@ -50,7 +50,7 @@ for tma in ("0", "1"):
             x = rng.uniform(-1, 1, (ch, pts)).astype(np.float32)
             assert c.convolution(y, x) == 0
             assert c.convolution(y, x, x * 0.1) == 0
-os.environ.pop("B2F_PCONV_TMA", None)
+eng.set_option("pconv_tma", -1)
 # direct convolution: single block (cluster tap split), multi-block (16 outputs per thread), ragged sizes, time-varying
 for irsize, vsize, ch, nb in ((4096, 256, 2, 1), (4096, 256, 2, 6), (100, 16, 3, 1), (64, 1, 2, 3)):
     d = eng.Cldconv(0, irsize, vsize, channels=ch, max_blocks=nb)
