@@ -169,6 +169,41 @@ int b2f_dconv_process_dev(b2f_dconv *h, void *d_out, const void *d_in, int nbloc
 int b2f_dconv_process_tv_host(b2f_dconv *h, float *out, const float *in1, const float *in2);
 int b2f_dconv_process_tv_dev(b2f_dconv *h, void *d_out, const void *d_in1, const void *d_in2, void *stream);
 
+/* ---- several GPUs behind one handle ------------------------------------------------
+ * The reference is one object = one channel = one device (cl_conv.cpp:154, cl_fft.cpp:49) and its
+ * callers are single processes (csound/opcode.cpp:172-203). A *_multi handle shards `channels`
+ * convolvers (or the transforms of a batch) over `ndev` CUDA devices in contiguous ranges --
+ * channels [g*channels/ndev, (g+1)*channels/ndev) live on devices[g] for their whole life -- with
+ * one stream and one host worker thread per device and NO inter-device communication. The host
+ * entry points have the single-device signatures and semantics; one call fans out
+ * H2D -> kernels -> D2H on all devices at once and returns when every device has finished.
+ * devices[] must be distinct ordinals; channels (max_batch) >= ndev. */
+typedef struct b2f_pconv_multi b2f_pconv_multi;
+int b2f_pconv_multi_create(b2f_pconv_multi **h, const int *devices, int ndev, int cvs, int pts, int channels);
+int b2f_pconv_multi_destroy(b2f_pconv_multi *h);
+int b2f_pconv_multi_nparts(const b2f_pconv_multi *h);
+int b2f_pconv_multi_reset(b2f_pconv_multi *h);
+int b2f_pconv_multi_push_ir_host(b2f_pconv_multi *h, const float *ir, size_t ir_stride);
+int b2f_pconv_multi_process_host(b2f_pconv_multi *h, float *out, const float *in);
+int b2f_pconv_multi_process_tv_host(b2f_pconv_multi *h, float *out, const float *in1, const float *in2);
+typedef struct b2f_dconv_multi b2f_dconv_multi;
+int b2f_dconv_multi_create(b2f_dconv_multi **h, const int *devices, int ndev, int irsize, int vsize, int channels,
+                           int max_blocks);
+int b2f_dconv_multi_destroy(b2f_dconv_multi *h);
+int b2f_dconv_multi_reset(b2f_dconv_multi *h);
+int b2f_dconv_multi_push_ir_host(b2f_dconv_multi *h, const float *ir, size_t ir_stride);
+int b2f_dconv_multi_process_host(b2f_dconv_multi *h, float *out, const float *in, int nblocks);
+int b2f_dconv_multi_process_tv_host(b2f_dconv_multi *h, float *out, const float *in1, const float *in2);
+/* transform b of a call's batch runs on devices[g], g*batch/ndev <= b < (g+1)*batch/ndev */
+typedef struct b2f_cfft_multi b2f_cfft_multi;
+int b2f_cfft_multi_create(b2f_cfft_multi **h, const int *devices, int ndev, int N, int fwd, int max_batch);
+int b2f_cfft_multi_destroy(b2f_cfft_multi *h);
+int b2f_cfft_multi_exec_host(b2f_cfft_multi *h, float *c, int batch);
+typedef struct b2f_rfft_multi b2f_rfft_multi;
+int b2f_rfft_multi_create(b2f_rfft_multi **h, const int *devices, int ndev, int size, int fwd, int max_batch);
+int b2f_rfft_multi_destroy(b2f_rfft_multi *h);
+int b2f_rfft_multi_exec_host(b2f_rfft_multi *h, float *c, float *r, int batch);
+
 #ifdef __cplusplus
 }
 #endif

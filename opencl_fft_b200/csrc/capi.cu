@@ -1416,3 +1416,5 @@ extern "C" int b2f_dconv_process_tv_host(b2f_dconv *h, float *out, const float *
   if ((rc = dconv_enqueue(h, h->d_out, h->d_in1, 1, h->stream))) return rc;
   return d2h(out, h->d_out, bytes, h->sg_out, h->stream);
 }
+
+#include "multi_gpu.inl"

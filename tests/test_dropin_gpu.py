@@ -50,3 +50,60 @@ def test_reference_test_rfft_prints_known_answer():
     vin = np.array([float(v) for v in _vector(out[1]).split(",")])
     vout = np.array([float(v) for v in _vector(out[3]).split(",")])
     assert np.abs(vin - vout).max() < 2e-3
+
+
+# ---- the convolution classes through C++ (include/cl_conv.h, include/cl_dconv.h over libcl_fft.so) ---------------------
+CONV = os.path.join(ROOT, "tests", "_bin", "conv_classes")
+
+
+def _conv_classes(tmp_path, args, files):
+    if not os.path.exists(CONV):
+        pytest.skip(f"{CONV} not built (python __graft_entry__.py)")
+    for name, arr in files.items():
+        np.ascontiguousarray(arr, np.float32).tofile(tmp_path / name)
+    res = subprocess.run([CONV, *map(str, args), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    return np.fromfile(tmp_path / "out.f32", np.float32), res.stdout
+
+
+def test_cpp_clpconv_static_matches_reference_golden(tmp_path):
+    """cl_conv::Clpconv(device, cvs, pts, errs, uData) + push_ir + convolution(out, in) from a C++ program: BASELINE
+    config 3 (96000 taps / 512) and the ring-wrapping small case, against the unmodified reference's output."""
+    from conftest import TOL, rel_l2
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    out, log = _conv_classes(tmp_path, ["pconv", 96000, 512, 12, 0], {"ir.f32": g["pconv_cfg3_ir"], "in.f32": g["pconv_cfg3_in"]})
+    assert "ok 12 blocks, 0 messages" in log
+    assert rel_l2(out.reshape(12, 512), g["pconv_cfg3_out"]) < TOL
+    out, _ = _conv_classes(tmp_path, ["pconv", 1000, 64, 40, 0], {"ir.f32": g["pconv_small_ir"], "in.f32": g["pconv_small_in"]})
+    assert rel_l2(out.reshape(40, 64), g["pconv_small_out"]) < TOL
+
+
+def test_cpp_clpconv_time_varying_matches_reference_golden(tmp_path):
+    from conftest import TOL, rel_l2
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    out, _ = _conv_classes(tmp_path, ["pconv", 1000, 64, 40, 1], {"in.f32": g["pconv_small_in"], "in2.f32": g["pconv_small_in2"]})
+    assert rel_l2(out.reshape(40, 64), g["pconv_small_tv_out"]) < TOL
+
+
+def test_cpp_cldconv_both_overloads_match_reference_golden(tmp_path):
+    from conftest import TOL, rel_l2
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    out, _ = _conv_classes(tmp_path, ["dconv", 4096, 256, 6, 0], {"ir.f32": g["dconv_cfg4_ir"], "in.f32": g["dconv_cfg4_in"]})
+    assert rel_l2(out.reshape(6, 256), g["dconv_cfg4_out"]) < TOL
+    # time-varying: the golden run pushes no IR (the coefficient ring is recorded from in2); push zeros here
+    out, _ = _conv_classes(tmp_path, ["dconv", 64, 16, 30, 1],
+                           {"ir.f32": np.zeros(64, np.float32), "in.f32": g["dconv_tv_in"], "in2.f32": g["dconv_tv_in2"]})
+    assert rel_l2(out.reshape(30, 16), g["dconv_tv_out"]) < TOL
+
+
+def test_cpp_failed_constructors_report_through_callback():
+    """A device that does not exist / a size the engine rejects: get_cl_err() > 0, the callback hears why, the methods
+    return the error instead of computing (reference convention, cl_conv.h:137-145; opcode.cpp:188,204 checks it)."""
+    if not os.path.exists(CONV):
+        pytest.skip(f"{CONV} not built")
+    res = subprocess.run([CONV, "failctor"], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "msg: CUDA device not found" in res.stdout and "msg: Invalid value" in res.stdout

@@ -296,3 +296,110 @@ def test_pipelined_host_call_equals_device_path(eng, options):
         assert c.convolution_dev(d_y, torch.from_numpy(x[t]).cuda()) == 0
         torch.cuda.synchronize()
         assert np.array_equal(d_y.cpu().numpy(), y_pipe[t])
+
+
+def test_benched_launch_configuration_vs_oracle(eng, port):
+    """The exact configuration bench.py times (BASELINE configs[4]): 1024 channels x 480000 taps x 512-sample
+    partitions = 937 partitions, which selects 2-CTA clusters. Four scattered channels against the oracle over three
+    blocks; IRs and inputs are generated on the device as the bench does and copied back for the oracle."""
+    import torch
+
+    channels, cvs, pts, nb = 1024, 480000, 512, 3
+    c = eng.Clpconv(0, cvs, pts, channels=channels)
+    assert c.get_cl_err() == 0 and c.nparts == 937
+    g = torch.Generator(device="cuda").manual_seed(7000)
+    n = torch.arange(cvs, device="cuda", dtype=torch.float32)
+    ir = torch.randn(channels, cvs, generator=g, device="cuda") * torch.exp(-6.9078 * n / cvs)
+    ir /= ir.norm(dim=1, keepdim=True)
+    assert c.push_ir_dev(ir, cvs) == 0
+    x = torch.rand(nb, channels, pts, generator=g, device="cuda") * 2 - 1
+    y = torch.empty(nb, channels, pts, device="cuda")
+    for t in range(nb):
+        assert c.convolution_dev(y[t], x[t]) == 0
+    torch.cuda.synchronize()
+    for k in (0, 341, 682, 1023):
+        o = port.pconv(cvs, pts)
+        o.push_ir(ir[k].cpu().numpy())
+        want = np.stack([o.convolution(x[t, k].cpu().numpy()) for t in range(nb)])
+        assert rel_l2(y[:, k].cpu().numpy(), want) < TOL, k
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_ring_wrap_for_every_cluster_size(eng, port, options, cluster):
+    """40 partitions split over clusters of 1 / 2 / 4 / 8 CTAs (option pconv_cluster), 2 * nparts + 2 blocks so that the
+    delay line wraps twice, static and time-varying, against the oracle."""
+    options("pconv_cluster", cluster)
+    pts, nparts, channels = 512, 40, 3
+    cvs, nb = nparts * pts, 2 * nparts + 2
+    rng = np.random.default_rng(cluster)
+    ir = (rng.standard_normal((channels, cvs)) * 0.05).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, channels, pts)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, channels, pts)) * 0.05).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts, channels=channels)
+    assert c.get_cl_err() == 0 and c.push_ir(ir) == 0
+    y = run_stream(c, x)
+    ctv = eng.Clpconv(0, cvs, pts, channels=channels)
+    ytv = run_stream(ctv, x, x2)
+    for k in (0, channels - 1):
+        o = port.pconv(cvs, pts)
+        o.push_ir(ir[k])
+        assert rel_l2(y[:, k], np.stack([o.convolution(x[t, k]) for t in range(nb)])) < TOL
+        o = port.pconv(cvs, pts)
+        assert rel_l2(ytv[:, k], np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])) < TOL
+
+
+def test_invalid_cluster_option_is_rejected_at_create(eng, options):
+    options("pconv_cluster", 3)
+    assert eng.Clpconv(0, 4096, 512, uData=1).get_cl_err() == 2
+    options("pconv_cluster", 8)
+    assert eng.Clpconv(0, 4 * 512, 512, uData=1).get_cl_err() == 2  # more CTAs than partitions
+
+
+@pytest.mark.parametrize("pts,channels", [(8192, 2), (32768, 1)])
+def test_graph_replay_equals_stream_launches(eng, port, options, pts, channels):
+    """General path (pts >= 8192, 7-9 launches per block): the host call replays the block as one CUDA graph over
+    device-resident ring positions. Same bits as the plain stream launches (option graph = 0), static and
+    time-varying, over enough blocks to wrap the rings; and the oracle's values."""
+    nparts = 3
+    cvs, nb = nparts * pts, 2 * nparts + 2
+    rng = np.random.default_rng(pts)
+    ir = (rng.standard_normal((channels, cvs)) * 0.05).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, channels, pts)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, channels, pts)) * 0.05).astype(np.float32)
+    res = {}
+    for graph in (1, 0):
+        options("graph", graph)
+        c = eng.Clpconv(0, cvs, pts, channels=channels)
+        assert c.get_cl_err() == 0 and c.push_ir(ir) == 0
+        ys = run_stream(c, x)
+        c.reset()  # the graph survives a reset: the ring positions it reads are device state
+        ys2 = run_stream(c, x)
+        assert np.array_equal(ys, ys2)
+        ctv = eng.Clpconv(0, cvs, pts, channels=channels)
+        res[graph] = (ys, run_stream(ctv, x, x2))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    o = port.pconv(cvs, pts)
+    o.push_ir(ir[0])
+    assert rel_l2(res[1][0][:, 0], np.stack([o.convolution(x[t, 0]) for t in range(nb)])) < TOL
+    o = port.pconv(cvs, pts)
+    assert rel_l2(res[1][1][:, 0], np.stack([o.convolution(x[t, 0], x2[t, 0]) for t in range(nb)])) < TOL
+
+
+def test_python_binding_rejects_short_buffers(eng):
+    """The C entry points read and write channels * pts floats behind the pointers they are given: the binding checks
+    the element counts first (B2F_ERR_INVALID_VALUE = 2) instead of letting the engine run off the arrays."""
+    c = eng.Clpconv(0, 4 * 64, 64, channels=3)
+    assert c.push_ir(np.zeros(3 * 4 * 64 - 1, np.float32)) == 2       # one float short
+    assert c.push_ir(np.zeros((2, 4 * 64), np.float32)) == 2          # a row missing
+    assert c.push_ir(np.zeros((3, 4 * 64), np.float32)) == 0
+    good, short = np.zeros((3, 64), np.float32), np.zeros((3, 63), np.float32)
+    assert c.convolution(short, good) == 2 and c.convolution(good, short) == 2
+    assert c.convolution(good, good, short) == 2
+    assert c.convolution(good, good) == 0 and c.convolution(good, good, good) == 0
+    d = eng.Cldconv(0, 32, 8, channels=2, max_blocks=4)
+    assert d.push_ir(np.zeros(63, np.float32)) == 2 and d.push_ir(np.zeros((2, 32), np.float32)) == 0
+    assert d.convolution(np.zeros((2, 16), np.float32), np.zeros((2, 32), np.float32), nblocks=4) == 2
+    assert d.convolution(np.zeros((2, 32), np.float32), np.zeros((2, 32), np.float32), nblocks=4) == 0
+    r = eng.Clrfft(0, 64, True)
+    assert r.transform(np.zeros(32, np.complex64), np.zeros(63, np.float32)) == 2
+    assert r.transform(np.zeros(32, np.complex64), np.zeros(64, np.float32)) == 0
