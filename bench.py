@@ -7,13 +7,17 @@ Headline workload (BASELINE.json configs[4], "metric" second half): partitioned 
 impulse responses (480,000 taps -> 937 partitions of 512 samples), 1024 channels per GPU, one distinct
 IR per channel. One "step" = one 512-sample streaming block for every channel (one fused kernel launch).
   value = real-time channels @ 48 kHz = channels * (512 / 48000 s) / t_step          (whole job, all GPUs)
-`--workload rfft` makes the other half of the metric (batched 1024 x 65536-point real FFT, GB/s) the
-headline instead; by default it is reported under "secondary" together with the batched 1024-point
-complex FFT and the direct convolution of config 4.
+The other half of the metric (batched 1024 x 65536-point real FFT, GB/s) is measured in the same run and reported
+as the "fft" object of the line -- value, roofline (achieved / peak / frac / traffic), end-to-end through the host API
+and, at N = 1, its own cpu_baseline; `--workload rfft` makes it the headline instead. "secondary" (N = 1) carries the
+batched 1024-point complex FFT, the config-2 round trip, the host-API latencies and the direct convolution of config 4.
 
 Multi-GPU (torchrun, one rank per GPU): channels are sharded, every rank owns all state of its channels,
 there is no data-path collective; NCCL carries only the barrier and the max-over-ranks of the step time.
-Scaling is weak: 1024 channels per GPU.
+The headline scaling is weak (1024 channels per GPU, 1024 transforms per GPU); the "strong" object is the literal
+BASELINE configs[4] split -- 1024 channels and 1024 transforms in total, 1024/N per GPU. "e2e_single_process" is the
+same weak workload driven by ONE process through the library's multi-GPU handle (devices=[0..N-1]: one worker thread
+and stream per device, include/b200fft.h), measured by rank 0 while the other ranks wait.
 
 `--impl reference` times the reference's own implementation on the host CPU cores: the unmodified
 reference sources compiled against oracle/minicl when oracle/_ref/libclfft_ref.so is present
@@ -40,6 +44,8 @@ CVS = 480000  # 10 s at 48 kHz -> 937 partitions (truncating)
 CHANNELS_PER_GPU = 1024
 RFFT_SIZE = 65536
 RFFT_BATCH = 1024
+RFFT_KERNEL = "fft_sm_kernel<false,kSmRealFwd> (one SM per transform, one HBM pass, split fused)"
+RFFT_KERNEL_SMALL = "large_cols_kernel<7,8> + large_rows_kernel<7,8,REAL> (four-step pair, < 96 transforms per call)"
 
 
 def measured_peaks():
@@ -165,7 +171,8 @@ def synth_ir_dev(channels, cvs, seed):
     return ir.contiguous()
 
 
-def bench_pconv(eng, local, rank, world, steps, warmup, channels=CHANNELS_PER_GPU, cvs=CVS, pts=PTS, e2e=True):
+def bench_pconv(eng, local, rank, world, steps, warmup, channels=CHANNELS_PER_GPU, cvs=CVS, pts=PTS, e2e=True,
+                spot_check=False):
     import numpy as np
     import torch
 
@@ -230,8 +237,88 @@ def bench_pconv(eng, local, rank, world, steps, warmup, channels=CHANNELS_PER_GP
         assert conv.convolution_dev(conv2_out, x[0]) == 0
         torch.cuda.synchronize()
         res["e2e_matches_device_path"] = bool(np.array_equal(conv2_out.cpu().numpy(), hy_np))
+        # the reference's API takes any pointer (cl_conv.cpp:399,455): the same call on pageable numpy buffers
+        px, py = np.array(hx_np[0]), np.empty((channels, pts), np.float32)
+        conv.reset()
+        for i in range(2):
+            assert conv.convolution(py, px) == 0
+        barrier()
+        n = max(3, min(steps, 20))
+        t0 = time.perf_counter()
+        for i in range(n):
+            assert conv.convolution(py, px) == 0
+        t1 = time.perf_counter()
+        barrier()
+        res["e2e_pageable_ms_per_step"] = max_over_ranks((t1 - t0) * 1e3) / n
+    if spot_check:
+        res["parity_spot_check"] = pconv_spot_check(conv, channels, cvs, pts, 7000 + rank)
     conv.close()
     return res
+
+
+def pconv_spot_check(conv, channels, cvs, pts, seed):
+    """Outside every timed region: two blocks of two channels of the benched handle against the CPU oracle
+    (relative L2; the parity contract is 1e-5)."""
+    import numpy as np
+    import torch
+
+    import oracle
+
+    P = oracle.port()
+    ir = synth_ir_dev(channels, cvs, seed)
+    picks = [0, channels - 1]
+    irs = {k: ir[k].cpu().numpy() for k in picks}
+    del ir
+    conv.reset()
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = (torch.rand(2, channels, pts, generator=g, device="cuda") * 2 - 1).contiguous()
+    y = torch.empty(2, channels, pts, device="cuda")
+    for t in range(2):
+        assert conv.convolution_dev(y[t], x[t]) == 0
+    torch.cuda.synchronize()
+    worst = 0.0
+    for k in picks:
+        o = P.pconv(cvs, pts)
+        o.push_ir(irs[k])
+        want = np.stack([o.convolution(x[t, k].cpu().numpy()) for t in range(2)]).astype(np.float64)
+        got = y[:, k].cpu().numpy().astype(np.float64)
+        worst = max(worst, float(np.linalg.norm(got - want) / np.linalg.norm(want)))
+    return {"rel_l2_vs_oracle": worst, "channels_checked": picks, "blocks": 2, "tolerance": 1e-5}
+
+
+def bench_pconv_single_process(eng, devices, steps, warmup, channels_per_gpu=CHANNELS_PER_GPU, cvs=CVS, pts=PTS):
+    """The weak workload through ONE multi-GPU handle in ONE process: host buffers in, host buffers out."""
+    import numpy as np
+    import torch
+
+    n = len(devices)
+    channels = channels_per_gpu * n
+    conv = eng.Clpconv(0, cvs, pts, channels=channels, devices=devices)
+    if conv.get_cl_err():
+        raise RuntimeError("Clpconv(devices=...): " + eng.cl_error_string(conv.get_cl_err()))
+    # the same decaying-noise IRs, generated on the host in float32 (1.9 GB per GPU's worth of channels)
+    rng = np.random.default_rng(7000)
+    env = np.exp(-6.9078 * np.arange(cvs, dtype=np.float32) / cvs)
+    ir = np.empty((channels, cvs), np.float32)
+    for c0 in range(0, channels, 64):
+        blk = rng.standard_normal((min(64, channels - c0), cvs), dtype=np.float32) * env
+        ir[c0:c0 + blk.shape[0]] = blk / np.linalg.norm(blk, axis=1, keepdims=True)
+    assert conv.push_ir(ir) == 0
+    del ir
+    hx = torch.empty(4, channels, pts).pin_memory()
+    hx.uniform_(-1, 1)
+    hy = torch.empty(channels, pts).pin_memory()
+    hx_np, hy_np = hx.numpy(), hy.numpy()
+    for i in range(warmup):
+        assert conv.convolution(hy_np, hx_np[i % 4]) == 0
+    t0 = time.perf_counter()
+    for i in range(steps):
+        assert conv.convolution(hy_np, hx_np[i % 4]) == 0
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    conv.close()
+    return {"value": channels * (pts / SR) / (ms * 1e-3), "unit": "realtime_channels_48k", "ms_per_step": ms,
+            "devices": n, "channels_total": channels, "h2d_bytes_per_step": channels * pts * 4,
+            "d2h_bytes_per_step": channels * pts * 4}
 
 
 def bench_rfft(eng, local, rank, world, steps, warmup, size=RFFT_SIZE, batch=RFFT_BATCH, e2e=False):
@@ -414,7 +501,7 @@ def cpu_baseline_pconv(threads, cvs=CVS, pts=PTS, blocks=None):
     impl = oracle.best()
     nparts = cvs // pts
     if blocks is None:
-        blocks = 160  # ~15 s of CPU work on 16 cores
+        blocks = 1600  # ~10 s wall on 16 cores
     rng = np.random.default_rng(7000)
     n = np.arange(cvs)
     ir = (rng.standard_normal((threads, cvs)) * np.exp(-6.9078 * n / cvs)).astype(np.float32)
@@ -432,19 +519,22 @@ def cpu_baseline_pconv(threads, cvs=CVS, pts=PTS, blocks=None):
     }
 
 
-def cpu_baseline_rfft(threads, size=RFFT_SIZE, batch=None):
+def cpu_baseline_rfft(threads, size=RFFT_SIZE, batch=None, reps=24):
+    """`reps` passes over a batch of 128 x threads transforms (512 MB of input at 16 threads): ~10 s of CPU work"""
     import numpy as np
 
     import oracle
 
     impl = oracle.best()
     if batch is None:
-        batch = 128 * threads  # ~10 s of CPU work
+        batch = 128 * threads
     rng = np.random.default_rng(6000)
     x = rng.uniform(-1, 1, (batch, size)).astype(np.float32)
-    secs, _ = impl.rfft_run(x, True, threads)
-    return {"value": batch * 8 * size / secs / 1e9, "unit": "GB/s", "cores": threads, "kind": impl.kind,
-            "sample": f"{batch} transforms of {size} real points, {secs:.2f} s wall", "seconds": secs}
+    secs = 0.0
+    for _ in range(reps):
+        secs += impl.rfft_run(x, True, threads)[0]
+    return {"value": reps * batch * 8 * size / secs / 1e9, "unit": "GB/s", "cores": threads, "kind": impl.kind,
+            "sample": f"{reps} x {batch} transforms of {size} real points, {secs:.2f} s wall", "seconds": secs}
 
 
 def run_reference_arm(args):
@@ -454,7 +544,7 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     fn = cpu_baseline_pconv if args.workload == "pconv" else cpu_baseline_rfft
-    small = {"blocks": 16} if args.workload == "pconv" else {"batch": 16 * threads}
+    small = {"blocks": 160} if args.workload == "pconv" else {"batch": 32 * threads, "reps": 4}
     for _ in range(args.warmup):
         fn(threads, **small)
     vals, secs = [], 0.0
@@ -490,6 +580,25 @@ def workload_config(workload):
             "parallelism": "transform batch sharded across GPUs, no collective"}
 
 
+def fft_objects(eng, local, rank, world, steps, warmup, peak, peak_src, batch, e2e):
+    """The FFT half of the metric: the line's `fft` object (value over all GPUs, roofline of this rank's launch)."""
+    f = bench_rfft(eng, local, rank, world, steps, warmup, batch=batch, e2e=e2e)
+    t = f["ms_per_step"] * 1e-3
+    achieved = f["bytes_per_step"] / t / 1e9
+    obj = {"metric": "batched_rfft_GBps", "value": f["bytes_per_step"] * world / t / 1e9, "unit": "GB/s",
+           "ms_per_step": f["ms_per_step"], "batch_per_gpu": batch, "size": RFFT_SIZE, "clocks": f["clocks"],
+           "gpu_launches": steps if batch >= 96 else 2 * steps,
+           "roofline": {"bound": "hbm", "kernel": RFFT_KERNEL if batch >= 96 else RFFT_KERNEL_SMALL, "achieved": achieved,
+                        "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": ncu_traffic("rfft65536_bytes_per_step") if batch == RFFT_BATCH else None,
+                        "algorithmic_bytes_per_launch": f["bytes_per_step"], "peak_source": peak_src}}
+    if e2e:
+        obj["e2e"] = {"value": f["bytes_per_step"] * world / (f["e2e_ms_per_step"] * 1e-3) / 1e9, "unit": "GB/s",
+                      "h2d_bytes_per_step": f["h2d_bytes_per_step"], "d2h_bytes_per_step": f["d2h_bytes_per_step"],
+                      "ms_per_step": f["e2e_ms_per_step"]}
+    return obj
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -497,8 +606,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pconv", choices=["pconv", "rfft"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="which split the headline value is: 1024 channels per GPU (weak) or 1024 in total (strong); "
+                         "the other one is reported beside it")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-process", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -512,44 +625,60 @@ def main():
 
     rank, world, local = dist_setup(args.gpus)
     peak, peak_src, sm_max = measured_peaks()
+    k = max(5, min(args.steps, 20))  # steps of the measurements that are not the headline
+    first = rank == 0 and world == 1
 
-    if args.workload == "pconv":
-        r = bench_pconv(eng, local, rank, world, args.steps, args.warmup)
-        t_step = r["ms_per_step"] * 1e-3
-        channels_total = r["channels_per_gpu"] * world
-        value = channels_total * (PTS / SR) / t_step
-        unit, metric = "realtime_channels_48k", "pconv_realtime_channels_48k"
+    # ---- partitioned convolution: weak (1024 channels per GPU) and the literal configs[4] split (1024 in total)
+    def pconv_obj(channels, steps, e2e, spot):
+        r = bench_pconv(eng, local, rank, world, steps, args.warmup, channels=channels, e2e=e2e, spot_check=spot)
+        t = r["ms_per_step"] * 1e-3
         achieved = r["bytes_per_launch"] / (r["ms_per_step_rank"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "pconv_step_kernel<9,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic("pconv_step_bytes_per_launch"),
-                "algorithmic_bytes_per_launch": r["bytes_per_launch"], "peak_source": peak_src}
-        e2e_v = channels_total * (PTS / SR) / (r["e2e_ms_per_step"] * 1e-3)
-        e2e = {"value": e2e_v, "unit": unit, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
-               "d2h_bytes_per_step": r["d2h_bytes_per_step"], "ms_per_step": r["e2e_ms_per_step"],
-               "same_bits_as_device_path": r["e2e_matches_device_path"]}
-        launches = r["launches"]
-    else:
-        r = bench_rfft(eng, local, rank, world, args.steps, args.warmup, e2e=True)
-        t_step = r["ms_per_step"] * 1e-3
-        value = r["bytes_per_step"] * world / t_step / 1e9
-        unit, metric = "GB/s", "batched_rfft_GBps"
-        achieved = r["bytes_per_step"] / t_step / 1e9
-        roof = {"bound": "hbm", "kernel": "large_cols_kernel<7,8> + large_rows_kernel<7,8,REAL> (split fused)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("rfft65536_bytes_per_step"),
-                "algorithmic_bytes_per_launch": r["bytes_per_step"], "peak_source": peak_src}
-        e2e_v = r["bytes_per_step"] * world / (r["e2e_ms_per_step"] * 1e-3) / 1e9
-        e2e = {"value": e2e_v, "unit": unit, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
-               "d2h_bytes_per_step": r["d2h_bytes_per_step"], "ms_per_step": r["e2e_ms_per_step"]}
-        launches = args.steps * 2  # per step: columns kernel + rows kernel (real split fused)
+        o = {"metric": "pconv_realtime_channels_48k", "value": channels * world * (PTS / SR) / t,
+             "unit": "realtime_channels_48k", "ms_per_step": r["ms_per_step"], "channels_per_gpu": channels,
+             "channels_total": channels * world, "clocks": r["clocks"], "gpu_launches": r["launches"],
+             "roofline": {"bound": "hbm", "kernel": "pconv_step_kernel<9,false>", "achieved": achieved, "peak": peak,
+                          "unit": "GB/s", "frac": achieved / peak,
+                          "traffic": ncu_traffic("pconv_step_bytes_per_launch") if channels == CHANNELS_PER_GPU else None,
+                          "algorithmic_bytes_per_launch": r["bytes_per_launch"], "peak_source": peak_src}}
+        if e2e:
+            o["e2e"] = {"value": channels * world * (PTS / SR) / (r["e2e_ms_per_step"] * 1e-3), "unit": o["unit"],
+                        "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"],
+                        "ms_per_step": r["e2e_ms_per_step"], "host_buffers": "pinned",
+                        "same_bits_as_device_path": r["e2e_matches_device_path"],
+                        "pageable_host_buffers": {"value": channels * world * (PTS / SR) / (r["e2e_pageable_ms_per_step"] * 1e-3),
+                                                  "ms_per_step": r["e2e_pageable_ms_per_step"]}}
+        if "parity_spot_check" in r:
+            o["parity_spot_check"] = r["parity_spot_check"]
+        return o
+
+    head_p = args.workload == "pconv"
+    strong_ch, strong_b = CHANNELS_PER_GPU // world, RFFT_BATCH // world
+    weak_p = pconv_obj(CHANNELS_PER_GPU, args.steps if head_p else k, True, first and not args.no_cpu_baseline)
+    strong_p = pconv_obj(strong_ch, k, False, False) if world > 1 else None
+    weak_f = fft_objects(eng, local, rank, world, args.steps if not head_p else k, 3, peak, peak_src, RFFT_BATCH, True)
+    strong_f = fft_objects(eng, local, rank, world, k, 3, peak, peak_src, strong_b, False) if world > 1 else None
+
+    def strong_view(o, weak):
+        if o is None:  # one GPU: the two splits coincide
+            o = weak
+        return {key: o[key] for key in ("metric", "value", "unit", "ms_per_step") if key in o} | {
+            "per_gpu": o.get("channels_per_gpu", o.get("batch_per_gpu")), "roofline_frac": o["roofline"]["frac"],
+            "kernel": o["roofline"]["kernel"]}
+
+    strong = {"note": "BASELINE configs[4] literally: 1024 channels / 1024 transforms in TOTAL, split evenly over the GPUs",
+              "pconv": strong_view(strong_p, weak_p), "rfft": strong_view(strong_f, weak_f)}
+
+    # ---- one process, all GPUs, through the library's multi-GPU handle (rank 0 alone; the others wait)
+    single = None
+    if rank == 0 and not args.no_single_process and head_p:
+        try:
+            single = bench_pconv_single_process(eng, list(range(world)), max(5, min(args.steps, 50)), 3)
+        except Exception as e:  # reported, never hidden
+            single = {"error": str(e)}
+    barrier()
 
     secondary = {}
-    if not args.no_secondary and rank == 0 and world == 1:
-        k = max(5, min(args.steps, 20))
-        if args.workload == "pconv":
-            f = bench_rfft(eng, local, rank, 1, k, 3)
-            gbs = f["bytes_per_step"] / (f["ms_per_step"] * 1e-3) / 1e9
-            secondary["batched_rfft_65536x1024"] = {"value": gbs, "unit": "GB/s", "ms_per_step": f["ms_per_step"],
-                                                    "roofline_frac": gbs / peak}
+    if not args.no_secondary and first:
         c = bench_cfft1024(eng, local, k, 3)
         gbs = c["bytes_per_step"] / (c["ms_per_step"] * 1e-3) / 1e9
         secondary["batched_cfft_1024x65536"] = {"value": gbs, "unit": "GB/s", "ms_per_step": c["ms_per_step"],
@@ -575,21 +704,43 @@ def main():
                                             "realtime_channels_48k": 64 * (375 * 256 / SR) / (d["ms_per_step"] * 1e-3),
                                             "single_block_latency_us": d["single_block_us"]}
 
-    cpu = None
-    if not args.no_cpu_baseline and rank == 0 and world == 1:
+    cpu = cpu_f = None
+    if not args.no_cpu_baseline and first:
         threads = os.cpu_count() or 1
-        cpu = cpu_baseline_pconv(threads) if args.workload == "pconv" else cpu_baseline_rfft(threads)
+        cpu = cpu_baseline_pconv(threads)
         cpu.pop("seconds", None)
+        cpu_f = cpu_baseline_rfft(threads)
+        cpu_f.pop("seconds", None)
+        weak_f["cpu_baseline"] = cpu_f
 
     if rank == 0:
+        strong_head = args.scaling == "strong" and world > 1
+        head = (strong_p if strong_head else weak_p) if head_p else (strong_f if strong_head else weak_f)
+        other = weak_f if head_p else weak_p
+        cfg = workload_config(args.workload)
+        if strong_head:
+            cfg["workload"] += f" -- STRONG split: {head.get('channels_per_gpu', head.get('batch_per_gpu'))} per GPU"
         line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload),
-            "clocks": r["clocks"], "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+            "metric": head["metric"], "value": head["value"], "unit": head["unit"], "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if strong_head else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg, "clocks": head["clocks"],
+            "e2e": head.get("e2e") or (weak_p if head_p else weak_f)["e2e"],
+            "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
         }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
+        if "parity_spot_check" in weak_p:
+            line["parity_spot_check"] = weak_p["parity_spot_check"]
+        if head_p:
+            line["fft"] = {kk: v for kk, v in other.items() if kk != "metric"} | {"metric": other["metric"]}
+            if cpu is not None:
+                line["cpu_baseline"] = cpu
+        else:
+            line["pconv"] = other
+            if cpu_f is not None:
+                line["cpu_baseline"] = cpu_f
+        line["strong"] = strong
+        if single is not None:
+            line["e2e_single_process"] = single
         if secondary:
             line["secondary"] = secondary
         print(json.dumps(line))

@@ -47,6 +47,26 @@ SYMBOLS = {
     "b2f_dconv_process_dev": (_i, [_vp, _vp, _vp, _i, _vp]),
     "b2f_dconv_process_tv_host": (_i, [_vp, _vp, _vp, _vp]),
     "b2f_dconv_process_tv_dev": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    # several GPUs behind one handle
+    "b2f_pconv_multi_create": (_i, [_pp, C.POINTER(_i), _i, _i, _i, _i]),
+    "b2f_pconv_multi_destroy": (_i, [_vp]),
+    "b2f_pconv_multi_nparts": (_i, [_vp]),
+    "b2f_pconv_multi_reset": (_i, [_vp]),
+    "b2f_pconv_multi_push_ir_host": (_i, [_vp, _vp, _sz]),
+    "b2f_pconv_multi_process_host": (_i, [_vp, _vp, _vp]),
+    "b2f_pconv_multi_process_tv_host": (_i, [_vp, _vp, _vp, _vp]),
+    "b2f_dconv_multi_create": (_i, [_pp, C.POINTER(_i), _i, _i, _i, _i, _i]),
+    "b2f_dconv_multi_destroy": (_i, [_vp]),
+    "b2f_dconv_multi_reset": (_i, [_vp]),
+    "b2f_dconv_multi_push_ir_host": (_i, [_vp, _vp, _sz]),
+    "b2f_dconv_multi_process_host": (_i, [_vp, _vp, _vp, _i]),
+    "b2f_dconv_multi_process_tv_host": (_i, [_vp, _vp, _vp, _vp]),
+    "b2f_cfft_multi_create": (_i, [_pp, C.POINTER(_i), _i, _i, _i, _i]),
+    "b2f_cfft_multi_destroy": (_i, [_vp]),
+    "b2f_cfft_multi_exec_host": (_i, [_vp, _vp, _i]),
+    "b2f_rfft_multi_create": (_i, [_pp, C.POINTER(_i), _i, _i, _i, _i]),
+    "b2f_rfft_multi_destroy": (_i, [_vp]),
+    "b2f_rfft_multi_exec_host": (_i, [_vp, _vp, _vp, _i]),
 }
 
 _lib = None

@@ -20,7 +20,7 @@ LIB_CLASSES = os.path.join(LIBDIR, "libcl_fft.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "g++"] + os.environ.get("B2F_NVCC_FLAGS", "").split()
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ccbin", "g++"] + os.environ.get("B2F_NVCC_FLAGS", "").split()
 
 
 def _newer(target: str, sources: list[str]) -> bool:
@@ -37,7 +37,7 @@ def _sources(*dirs: str) -> list[str]:
             continue
         for f in sorted(os.listdir(d)):
             p = os.path.join(d, f)
-            if os.path.isfile(p) and f.endswith((".cu", ".cuh", ".h", ".cpp")):
+            if os.path.isfile(p) and f.endswith((".cu", ".cuh", ".h", ".cpp", ".inl")):
                 out.append(p)
     return out
 

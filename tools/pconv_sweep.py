@@ -59,6 +59,17 @@ def run(channels, cvs, pts, steps=100, tv=False):
     return row
 
 
+if len(sys.argv) == 2 and sys.argv[1] == "--cluster-sweep":
+    # the strong-scaling regime (1024 channels split over 8 GPUs -> 128 per GPU) and its neighbours: the measured
+    # choice of the cluster split (0) against every forced split
+    for ch, cvs, pts in ((64, 96000, 512), (128, 96000, 512), (256, 96000, 512), (64, 480000, 512), (128, 480000, 512),
+                         (256, 480000, 512), (512, 480000, 512), (256, 480000, 4096), (1024, 480000, 4096),
+                         (16, 480000, 2048), (64, 480000, 2048)):
+        for S in (0, 1, 2, 4, 8):
+            eng.set_option("pconv_cluster", S)
+            r = run(ch, cvs, pts, steps=30)
+    eng.set_option("pconv_cluster", 0)
+    sys.exit(0)
 if len(sys.argv) == 4:  # one configuration: channels ir_taps partition
     run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), steps=30)
     sys.exit(0)
