@@ -130,7 +130,21 @@ def dist_setup(n_gpus):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a CPU-only rendezvous for the phase in which rank 0 alone drives every GPU through the library's multi-GPU
+        # handle: an NCCL barrier would park a spinning kernel on the other ranks' GPUs for its whole duration
+        global _CPU_GROUP
+        _CPU_GROUP = dist.new_group(backend="gloo")
     return rank, world, local
+
+
+_CPU_GROUP = None
+
+
+def cpu_barrier():
+    import torch.distributed as dist
+
+    if _CPU_GROUP is not None:
+        dist.barrier(group=_CPU_GROUP)
 
 
 def barrier():
@@ -670,11 +684,13 @@ def main():
 
     # ---- one process, all GPUs, through the library's multi-GPU handle (rank 0 alone; the others wait)
     single = None
+    barrier()
     if rank == 0 and not args.no_single_process and head_p:
         try:
             single = bench_pconv_single_process(eng, list(range(world)), max(5, min(args.steps, 50)), 3)
         except Exception as e:  # reported, never hidden
             single = {"error": str(e)}
+    cpu_barrier()
     barrier()
 
     secondary = {}

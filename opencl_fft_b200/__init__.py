@@ -142,6 +142,8 @@ class Clcfft:
         return lib().b2f_cfft_exec_dev(self._h, _dptr(d_in), _dptr(d_out), batch, _stream(stream))
 
     def close(self):
+        if C is None:  # interpreter shutdown: the module globals are already gone
+            return
         if getattr(self, "_h", None) and self._h.value:
             (lib().b2f_cfft_multi_destroy if self._multi else lib().b2f_cfft_destroy)(self._h)
             self._h = C.c_void_p()
@@ -187,6 +189,8 @@ class Clrfft:
         return lib().b2f_rfft_exec_dev(self._h, _dptr(d_in), _dptr(d_out), batch, _stream(stream))
 
     def close(self):
+        if C is None:  # interpreter shutdown: the module globals are already gone
+            return
         if getattr(self, "_h", None) and self._h.value:
             (lib().b2f_rfft_multi_destroy if self._multi else lib().b2f_rfft_destroy)(self._h)
             self._h = C.c_void_p()
@@ -279,6 +283,8 @@ class Clpconv:
         return out
 
     def close(self):
+        if C is None:  # interpreter shutdown: the module globals are already gone
+            return
         if getattr(self, "_h", None) and self._h.value:
             self._f[4](self._h)
             self._h = C.c_void_p()
@@ -359,6 +365,8 @@ class Cldconv:
         return self._f[3](self._h)
 
     def close(self):
+        if C is None:  # interpreter shutdown: the module globals are already gone
+            return
         if getattr(self, "_h", None) and self._h.value:
             self._f[4](self._h)
             self._h = C.c_void_p()
