@@ -817,10 +817,12 @@ static int launch_pconv_step_tt(const PconvArgs &a, int channels, int S, cudaStr
 template <int LOGP, bool TV>
 static int launch_pconv_step_t(const PconvArgs &a, int channels, int S, int tma_opt, cudaStream_t st) {
   // Which MAC feeds the fused kernel: registers (128-bit loads, 16 in flight per thread) or the TMA ring. Measured on
-  // B200 (256 channels x 480000 taps, TB/s, registers vs TMA): pts 512 7.28 vs 6.88; pts 1024 6.36 vs 6.03 (registers
-  // since the MAC walks each partition's whole frame at once); pts 2048 4.65 vs 6.07; pts 4096 4.09 vs 3.86 (4.43 at
-  // 1024 channels, where TMA wins). Option pconv_tma = 0 | 1 forces one or the other.
-  const bool use_tma = tma_opt >= 0 ? tma_opt == 1 : ((LOGP == 11 && channels >= 64) || (LOGP == 12 && channels >= 512));
+  // B200 (480000 taps, fraction of the measured HBM peak, registers vs TMA; tools/pconv_sweep.py --feed-sweep,
+  // profiles/r02_pconv_feed_sweep.txt): pts 512 1.10 vs 1.05; pts 1024 0.47 / 0.76 / 0.85 / 1.02 vs 0.40 / 0.66 /
+  // 0.75 / 0.95 at 16 / 64 / 256 / 1024 channels; pts 2048 0.29 / 0.53 / 0.71 / 0.84 vs 0.40 / 0.76 / 0.97 / 0.97;
+  // pts 4096 0.21 / 0.44 / 0.63 / 0.63 vs 0.23 / 0.46 / 0.68 / 0.78 -- the TMA feed walks every frame front to back
+  // (partition-major), the register feed of an 8-tile frame cannot. Option pconv_tma = 0 | 1 forces one or the other.
+  const bool use_tma = tma_opt >= 0 ? tma_opt == 1 : LOGP >= 11;
   return use_tma ? launch_pconv_step_tt<LOGP, TV, true>(a, channels, S, st)
                  : launch_pconv_step_tt<LOGP, TV, false>(a, channels, S, st);
 }

@@ -42,7 +42,8 @@ struct PconvGeom {
   static constexpr int TILES = (HALF + NTHREADS - 1) / NTHREADS;
   static constexpr int FFT_SMEM = VT * G::SMEM;            // float2 entries per FFT work buffer
   // TMA-fed MAC: one extra (producer) warp, a ring of STAGES x {FDL slice, IR slice} of SLICE float4 each
-  static constexpr int STAGES = 6;
+  // (4096-sample partitions leave room for one CTA per SM only: a deeper ring keeps enough bytes in flight)
+  static constexpr int STAGES = LOGP >= 12 ? 10 : 6;  // (10: the time-varying variant, with two FFT buffers, still fits 227 KB)
   static constexpr int SLICE = HALF < NTHREADS ? HALF : NTHREADS;  // float4 per slice (16 B .. 4 KB)
   static constexpr int RING_F4 = 2 * STAGES * SLICE;
 };
@@ -254,10 +255,10 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
   const int p_newg = TV ? a.wp2 : -1;
   const size_t stride4 = HALF;
 
-  if constexpr (!TMA && (P::TILES == 2 || P::TILES == 4)) {
-    // ---- register-fed, frame 2 or 4 times wider than the CTA: all tiles of a partition together (measured, 256
-    // channels x 480000 taps: pts 1024 4.48 -> 6.36 TB/s, pts 2048 4.14 -> 4.65; pts 4096 (8 tiles) 4.09 -> 3.78,
-    // so that size keeps the tile-by-tile sweep below) ------------------------------------------------------
+  if constexpr (P::TILES > 1 && (TMA || P::TILES == 2 || P::TILES == 4)) {
+    // ---- a frame several times wider than the CTA: all tiles of a partition together, one accumulator per tile.
+    // Register-fed (measured, 256 channels x 480000 taps: pts 1024 4.48 -> 6.36 TB/s, pts 2048 4.14 -> 4.65; pts 4096
+    // (8 tiles) 4.09 -> 3.78, so the register-fed 8-tile case keeps the tile-by-tile sweep below) or TMA-fed -----
     constexpr int TL = P::TILES;
     float4 acc[TL];
 #pragma unroll
@@ -265,21 +266,64 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
     float2 acc0 = make_float2(0.f, 0.f);
     const float4 *F = reinterpret_cast<const float4 *>(fdl) + tid;
     const float4 *Gp = reinterpret_cast<const float4 *>(irs) + tid;
-    int p = p_lo;
-    while (p < p_hi) {
-      if (p == p_newx || p == p_newg) {
-        p++;
-        continue;
+    if constexpr (TMA) {
+      // TMA-fed, partition-major: the producer streams every frame front to back -- tile after tile of partition p,
+      // then partition p + 1 -- so HBM sees two sequential streams per CTA, and the consumers keep one accumulator
+      // per tile in registers. (Round 1 swept all partitions once per tile, 4 KB slices 32 KB apart at pts 4096:
+      // 0.63-0.68 of the measured HBM peak.) Every thread walks the same (p, tile) sequence, so `slot` advances
+      // identically in the producer and in the consumers.
+      constexpr uint32_t kSliceBytes = P::SLICE * (uint32_t)sizeof(float4);
+      const unsigned char *Fb = reinterpret_cast<const unsigned char *>(fdl);
+      const unsigned char *Gb = reinterpret_cast<const unsigned char *>(irs);
+      const size_t frame_bytes = (size_t)PTS * sizeof(float2);
+      for (int p = p_lo; p < p_hi; p++) {
+        if (p == p_newx || p == p_newg) continue;
+        const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
+#pragma unroll
+        for (int t = 0; t < TL; t++) {
+          const uint32_t s = slot % P::STAGES, round = slot / P::STAGES;
+          slot++;
+          if (!worker) {
+            if ((tid & 31) == 0) {
+              if (round > 0) tma::mbar_wait(bar_empty + 8 * s, (round - 1) & 1);  // consumers released the stage
+              tma::mbar_expect_tx(bar_full + 8 * s, 2 * kSliceBytes);
+              tma::bulk_g2s(tma::smem_u32(ring + (2 * s) * P::SLICE), Fb + (size_t)frame * frame_bytes + t * kSliceBytes,
+                            kSliceBytes, bar_full + 8 * s);
+              tma::bulk_g2s(tma::smem_u32(ring + (2 * s + 1) * P::SLICE), Gb + (size_t)p * frame_bytes + t * kSliceBytes,
+                            kSliceBytes, bar_full + 8 * s);
+            }
+          } else {
+            tma::mbar_wait(bar_full + 8 * s, round & 1);
+            const float4 fa = ring[(2 * s) * P::SLICE + tid], gb = ring[(2 * s + 1) * P::SLICE + tid];
+            cmac2(acc[t], fa, gb);
+            if (t == 0) {
+              acc0.x += fa.x * gb.x;
+              acc0.y += fa.y * gb.y;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) tma::mbar_arrive(bar_empty + 8 * s);
+          }
+        }
       }
-      int end = p_hi;
-      if (p_newx > p && p_newx < end) end = p_newx;
-      if (p_newg > p && p_newg < end) end = p_newg;
-      const int wrap = nparts - rp;  // first p whose FDL frame index wraps to 0
-      if (wrap > p && wrap < end) end = wrap;
-      const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
-      mac_segment_tiles<TL, NT>(acc, acc0, F + (size_t)frame * stride4, Gp + (size_t)p * stride4, end - p, stride4);
-      p = end;
+      __syncwarp();  // the producer warp's lane 0 rejoins its warp before the next (aligned) barrier
+    } else {
+      int p = p_lo;
+      while (p < p_hi) {
+        if (p == p_newx || p == p_newg) {
+          p++;
+          continue;
+        }
+        int end = p_hi;
+        if (p_newx > p && p_newx < end) end = p_newx;
+        if (p_newg > p && p_newg < end) end = p_newg;
+        const int wrap = nparts - rp;  // first p whose FDL frame index wraps to 0
+        if (wrap > p && wrap < end) end = wrap;
+        const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
+        mac_segment_tiles<TL, NT>(acc, acc0, F + (size_t)frame * stride4, Gp + (size_t)p * stride4, end - p, stride4);
+        p = end;
+      }
     }
+    if (worker) {
 #pragma unroll
     for (int t = 0; t < TL; t++) {
       const int q = t * NT + tid;
@@ -318,9 +362,10 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
       }
       if (S > 1) sP[q] = acc[t];
     }
+    }
     if (S > 1) {
       cluster.sync();  // all partials visible cluster-wide
-      if (rank == 0) {
+      if (rank == 0 && worker) {
 #pragma unroll
         for (int t = 0; t < TL; t++) {
           for (int r = 1; r < S; r++) {
@@ -334,7 +379,7 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
       }
       cluster.sync();  // remote reads done before anyone exits
     }
-    if (rank == 0) {
+    if (rank == 0 && worker) {
 #pragma unroll
       for (int t = 0; t < TL; t++) sP[HALF + t * NT + tid] = acc[t];  // parked; moved to sX after the barrier below
     }

@@ -244,7 +244,7 @@ def test_time_varying_multichannel(eng, port):
 
 
 @pytest.mark.parametrize("tma", [0, 1])
-@pytest.mark.parametrize("pts,channels", [(64, 3), (512, 70), (1024, 70), (2048, 2), (8192, 2)])
+@pytest.mark.parametrize("pts,channels", [(64, 3), (512, 70), (1024, 70), (2048, 2), (4096, 3), (8192, 2)])
 def test_both_mac_feeds(eng, port, options, tma, pts, channels):
     """The spectral multiply-accumulate exists twice: fed by 128-bit register loads and fed by the TMA engine
     (cp.async.bulk into an mbarrier ring). The library picks by shape; option pconv_tma forces either. Both must

@@ -70,6 +70,15 @@ if len(sys.argv) == 2 and sys.argv[1] == "--cluster-sweep":
             r = run(ch, cvs, pts, steps=30)
     eng.set_option("pconv_cluster", 0)
     sys.exit(0)
+if len(sys.argv) == 2 and sys.argv[1] == "--feed-sweep":
+    # register-fed against TMA-fed MAC for the partitions wider than the CTA
+    for pts in (1024, 2048, 4096):
+        for ch in (16, 64, 256, 1024):
+            for tma in (0, 1):
+                eng.set_option("pconv_tma", tma)
+                r = run(ch, 480000, pts, steps=20)
+    eng.set_option("pconv_tma", -1)
+    sys.exit(0)
 if len(sys.argv) == 4:  # one configuration: channels ir_taps partition
     run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), steps=30)
     sys.exit(0)
