@@ -331,44 +331,54 @@ static int launch_rfft(int logn, bool inv, const float2 *in, float2 *out, const 
 }
 
 
-// ---- one-SM plan (fft_sm.cuh): N = 2^15 in one pass over HBM, one persistent CTA per SM ------------------------------
+// ---- one-SM plan (fft_sm.cuh): N = 2^15 (and complex N = 2^14) in one pass over HBM, one persistent CTA per SM -----------
 struct SmPlan {
-  int grid = 0;
-  float2 *d_twb = nullptr, *d_twa = nullptr;
-  bool ok() const { return d_twb != nullptr; }
-  // A transform takes one SM ~25 us whatever the batch, so below ~100 transforms the four-step launch pair, which
+  int grid = 0, logn = 0;
+  float2 *d_twn = nullptr, *d_twp = nullptr, *d_twa = nullptr;
+  bool ok() const { return d_twn != nullptr; }
+  // A transform takes one SM ~25 us whatever the batch, so below ~100 transforms per call the four-step launch pair, which
   // spreads every transform over the whole GPU, is the faster one (measured crossover, tools/fft_sm_probe.py).
+  // N = 2^14 runs two transforms per CTA iteration: twice the batch before the GPU is full.
   long long min_batch = 96;
-  bool use_for(int batch) const { return ok() && min_batch > 0 && batch >= min_batch; }
-  int init(int device) {
-    const int N = SmGeom::N;
-    std::vector<float2> twn(5 * 32), twa(5 * 32);
+  bool use_for(int batch) const { return ok() && min_batch > 0 && batch >= min_batch * (logn == 14 ? 2 : 1); }
+  int init(int device, int logn_) {
+    logn = logn_;
+    const int N = 1 << logn;
+    std::vector<float2> twn(5 * 32), twp(5 * 32), twa(5 * 32);
     for (int b = 0; b < 5; b++)
       for (int j = 0; j < 32; j++) {
-        twn[b * 32 + j] = ref_twiddle((long long)j << b, N);         // W_N^(j 2^b)
-        twa[b * 32 + j] = ref_twiddle((long long)(32 * j) << b, N);  // W_1024^(j 2^b)
+        twn[b * 32 + j] = ref_twiddle(((long long)j << b) % N, N);                       // W_N^(j 2^b)
+        twp[b * 32 + j] = ref_twiddle(((long long)(32 * j) << b) % N, N);                // W_N^(32 j 2^b)
+        twa[b * 32 + j] = ref_twiddle(((long long)(N / 1024) * j << b) % N, N);          // W_1024^(j 2^b)
       }
     int rc;
-    if ((rc = upload(twn, &d_twb)) || (rc = upload(twa, &d_twa))) return rc;
+    if ((rc = upload(twn, &d_twn)) || (rc = upload(twp, &d_twp)) || (rc = upload(twa, &d_twa))) return rc;
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
     grid = nsm > 0 ? nsm : 1;
     return B2F_OK;
   }
   void destroy() {
-    for (void *p : {(void *)d_twb, (void *)d_twa})
+    for (void *p : {(void *)d_twn, (void *)d_twp, (void *)d_twa})
       if (p) cudaFree(p);
-    d_twb = d_twa = nullptr;
+    d_twn = d_twp = d_twa = nullptr;
+  }
+  template <bool INV, int KIND, int LOG1>
+  int run_t(const float2 *in, float2 *out, const float2 *hw, int batch, float scale, cudaStream_t st) {
+    auto kern = fft_sm_kernel<INV, KIND, LOG1>;
+    int rc = set_smem(kern, SmGeom::SMEM);
+    if (rc) return rc;
+    const int units = (batch + (32 >> LOG1) - 1) / (32 >> LOG1);
+    const int g = units < grid ? units : grid;
+    kern<<<g, SmGeom::THREADS, SmGeom::SMEM, st>>>(in, out, d_twn, d_twp, d_twa, hw, batch, scale);
+    CK(cudaGetLastError());
+    return B2F_OK;
   }
   template <bool INV, int KIND>
   int run(const float2 *in, float2 *out, const float2 *hw, int batch, float scale, cudaStream_t st) {
-    auto kern = fft_sm_kernel<INV, KIND>;
-    int rc = set_smem(kern, SmGeom::SMEM);
-    if (rc) return rc;
-    const int g = batch < grid ? batch : grid;
-    kern<<<g, SmGeom::THREADS, SmGeom::SMEM, st>>>(in, out, d_twb, d_twa, hw, batch, scale);
-    CK(cudaGetLastError());
-    return B2F_OK;
+    if constexpr (KIND == kSmComplex)
+      if (logn == 14) return run_t<INV, KIND, 4>(in, out, hw, batch, scale, st);
+    return run_t<INV, KIND, 5>(in, out, hw, batch, scale, st);
   }
 };
 
@@ -573,9 +583,9 @@ struct FftPlanCore {
       rc = upload(make_pass_twiddles(logn), &d_tw);
       if (rc) return rc;
     }
-    if (logn == SmGeom::LOGN && opt.fft_sm_min_batch > 0) {
+    if ((logn == SmGeom::LOGN || (logn == 14 && !real)) && opt.fft_sm_min_batch > 0) {
       sm.min_batch = opt.fft_sm_min_batch;
-      rc = sm.init(dev);
+      rc = sm.init(dev, logn);
       if (rc) return rc;
     }
     if (real) {

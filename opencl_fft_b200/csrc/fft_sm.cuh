@@ -107,15 +107,32 @@ __device__ __forceinline__ void dft32(float2 (&v)[32]) {
 // built depth-first over the bits of m, so at most four partial products are alive at a time (26 complex
 // multiplications, at most four roundings deep, ~3e-7) -- the full table of a pass would be 31 loads per
 // butterfly through the LSU data pipe, which is the SM-side limit of the FFT kernels (fft_core.cuh).
-template <int BIT, int M, bool HAVE>
+template <int BIT, int M, bool HAVE, int OFF = 0>
 __device__ __forceinline__ void tw_tree(float2 (&v)[32], float2 p, const float2 (&base)[5]) {
   if constexpr (BIT < 0) {
-    if constexpr (HAVE) v[M] = cmul(v[M], p);
+    if constexpr (HAVE) v[OFF + M] = cmul(v[OFF + M], p);
   } else {
-    tw_tree<BIT - 1, M, HAVE>(v, p, base);
+    tw_tree<BIT - 1, M, HAVE, OFF>(v, p, base);
     float2 q = base[BIT];
     if constexpr (HAVE) q = cmul(p, q);
-    tw_tree<BIT - 1, (M | (1 << BIT)), true>(v, q, base);
+    tw_tree<BIT - 1, (M | (1 << BIT)), true, OFF>(v, q, base);
+  }
+}
+// two independent 16-point butterflies on v[0..15] and v[16..31] (N = 2^14: two transforms per unit)
+template <bool INV>
+__device__ __forceinline__ void dft16x2(float2 (&v)[32]) {
+  float2 a[16], b[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    a[i] = v[i];
+    b[i] = v[16 + i];
+  }
+  dft16<INV>(a);
+  dft16<INV>(b);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    v[i] = a[i];
+    v[16 + i] = b[i];
   }
 }
 
@@ -164,7 +181,7 @@ __device__ __forceinline__ void wait_ld8(float2 (&v)[8]) {
 
 // ---- geometry ---------------------------------------------------------------------------------------------------------
 struct SmGeom {
-  static constexpr int LOGN = 15, N = 1 << LOGN;
+  static constexpr int LOGN = 15, N = 1 << LOGN;  // (LOG1 = 4: N = 2^14, two transforms per unit)
   static constexpr int THREADS = 512;
   // exchange layout of a row (written by pass A, read by pass B): [k2][j3] float2, 16 bytes of padding per k2 line
   // and 16 per row: pass B's 128-bit reads (8 lanes = 8 rows, or 8 rows of the other k2) and pass A's 64-bit writes
@@ -175,7 +192,8 @@ struct SmGeom {
   static constexpr int OFF_SP = 16 * ROW;             // staging of P1's round 1, runs j1 = 16..31 (64 KiB + 256 B)
   static constexpr int OFF_Z = OFF_SP + 16 * RUN_C2R; // row k1 = 0 of the real transform, [k2][k3] float2
   static constexpr int OFF_TWN = OFF_Z + 1024 * 8;    // P1 twiddle bases [5][32]: W_N^(j3 2^b)
-  static constexpr int OFF_TWA = OFF_TWN + 5 * 32 * 8;  // pass-A twiddle bases [5][32]: W_1024^(j 2^b) (also W_N^(32 j2 2^b))
+  static constexpr int OFF_TWP = OFF_TWN + 5 * 32 * 8;  // P1 twiddle bases [5][32]: W_N^(32 j2 2^b)
+  static constexpr int OFF_TWA = OFF_TWP + 5 * 32 * 8;  // pass-A twiddle bases [5][32]: W_1024^(j 2^b)
   static constexpr int OFF_HW = OFF_TWA + 5 * 32 * 8;   // folded split table, entries 0..1023
   static constexpr int OFF_HW32 = OFF_HW + 1024 * 8;    // folded split table, entries 32 m (row k1 = 0)
   static constexpr int OFF_MISC = OFF_HW32 + 512 * 8;
@@ -223,21 +241,29 @@ __device__ constexpr float kSplitS[32] = {
 // staged in both (runs of 514 columns). Every thread reads its own column and the mirrored one from the staged runs and
 // keeps its own member of each pair. In the rows, the column groups j2 are stored permuted (0..7, 24..31, 8..23) so
 // that round 0 still writes the first halves and round 1 the second.
+//
+// LOG1 = 4 (N = 16 x 32 x 32 = 2^14, complex only): the same kernel carries TWO transforms per unit of work -- the 32
+// staged runs are the 16 runs of each, P1 is two radix-16 butterflies per column, job 0 is the first transform's 16
+// rows and job 1 the second's (parked in tensor memory meanwhile); passes A and B are unchanged.
 enum { kSmComplex = 0, kSmRealFwd = 1, kSmRealInv = 2 };
-template <bool INV, int KIND>
+template <bool INV, int KIND, int LOG1 = 5>
 __global__ void __launch_bounds__(SmGeom::THREADS, 1)
-    fft_sm_kernel(const float2 *in, float2 *out, const float2 *__restrict__ twn_g, const float2 *__restrict__ twa_g,
-                  const float2 *__restrict__ hw, int batch, float scale) {
+    fft_sm_kernel(const float2 *in, float2 *out, const float2 *__restrict__ twn_g, const float2 *__restrict__ twp_g,
+                  const float2 *__restrict__ twa_g, const float2 *__restrict__ hw, int batch, float scale) {
   using G = SmGeom;
   constexpr bool REAL = (KIND == kSmRealFwd), C2R = (KIND == kSmRealInv);
   static_assert(!(REAL && INV) && !(C2R && !INV), "the split follows a forward, the unsplit precedes an inverse transform");
-  constexpr int N = G::N;
+  static_assert(LOG1 == 5 || (LOG1 == 4 && KIND == kSmComplex), "two transforms per unit: complex only");
+  constexpr int N1 = 1 << LOG1, NTR = 32 / N1;  // radix of P1, transforms per unit
+  constexpr int N = N1 * 1024;
+  const int units = (batch + NTR - 1) / NTR;
   constexpr int TCOLS = REAL ? G::TCOLS_THREAD_R : G::TCOLS_THREAD_C;
   extern __shared__ __align__(16) unsigned char smraw[];
   unsigned char *rows = smraw;
   float2 *Z = reinterpret_cast<float2 *>(smraw + G::OFF_Z);
   unsigned char *sp = smraw + G::OFF_SP;
   float2 *twn = reinterpret_cast<float2 *>(smraw + G::OFF_TWN);
+  float2 *twp = reinterpret_cast<float2 *>(smraw + G::OFF_TWP);
   float2 *twa = reinterpret_cast<float2 *>(smraw + G::OFF_TWA);
   float2 *hwb = reinterpret_cast<float2 *>(smraw + G::OFF_HW);
   float2 *hw32 = reinterpret_cast<float2 *>(smraw + G::OFF_HW32);
@@ -246,6 +272,7 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
 
   if (tid < 5 * 32) {
     twn[tid] = __ldg(&twn_g[tid]);
+    twp[tid] = __ldg(&twp_g[tid]);
     twa[tid] = __ldg(&twa_g[tid]);
   }
   if constexpr (REAL || C2R)
@@ -271,8 +298,12 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   auto run_base = [&](int round, int j) -> unsigned char * {
     return round == 0 ? rows + j * RUN : (j < 16 ? rows + j * G::ROW + 4096 : sp + (j - 16) * RUN);
   };
-  auto stage_round = [&](int round, int tn) {  // the 32 lanes of one warp, one run each
-    const float2 *nx = in + (size_t)tn * N + 1024 * lane;
+  auto stage_round = [&](int round, int un) {  // the 32 lanes of one warp, one run each
+    // run `lane` of unit `un`: run lane % N1 of its transform lane / N1 (past the batch: the last transform again,
+    // its results are not stored)
+    int tr = un * NTR + lane / N1;
+    tr = tr < batch ? tr : batch - 1;
+    const float2 *nx = in + (size_t)tr * N + 1024 * (lane % N1);
     const uint32_t mb = round ? m_full1 : m_full0;
     const uint32_t d = tma::smem_u32(run_base(round, lane));
 #ifdef B2F_SMX_NO_LOAD
@@ -300,9 +331,9 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   if (warp == 0) stage_round(0, blockIdx.x);
   uint32_t par = 0;
 
-  for (int t = blockIdx.x; t < batch; t += gridDim.x, par ^= 1) {
-    float2 *dst = out + (size_t)t * N;
-    const bool more = t + (int)gridDim.x < batch;
+  for (int t = blockIdx.x; t < units; t += gridDim.x, par ^= 1) {
+    float2 *dst = out + (size_t)t * NTR * N;
+    const bool more = t + (int)gridDim.x < units;
 
     // ---- P1: radix-32 over j1 for columns c = tid, tid + 512 ------------------------------------------------------
 #pragma unroll
@@ -352,12 +383,18 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
       // W_N^(c 2^b), c = 32 j2 + j3, as the product of two table entries
       float2 base[5];
 #pragma unroll
-      for (int b = 0; b < 5; b++) {
-        base[b] = cmul(twa[b * 32 + (c >> 5)], twn[b * 32 + (c & 31)]);
+      for (int b = 0; b < LOG1; b++) {
+        base[b] = cmul(twp[b * 32 + (c >> 5)], twn[b * 32 + (c & 31)]);
         if (INV) base[b].y = -base[b].y;
       }
-      B2F_SMX_FFT(dft32<INV>(v));
-      B2F_SMX_FFT((tw_tree<4, 0, false>(v, make_float2(1.f, 0.f), base)));
+      if constexpr (LOG1 == 5) {
+        B2F_SMX_FFT(dft32<INV>(v));
+        B2F_SMX_FFT((tw_tree<4, 0, false>(v, make_float2(1.f, 0.f), base)));
+      } else {
+        B2F_SMX_FFT(dft16x2<INV>(v));
+        B2F_SMX_FFT((tw_tree<3, 0, false, 0>(v, make_float2(1.f, 0.f), base)));
+        B2F_SMX_FFT((tw_tree<3, 0, false, 16>(v, make_float2(1.f, 0.f), base)));
+      }
 #pragma unroll
       for (int s = 0; s < 16; s++) *reinterpret_cast<float2 *>(rows + s * G::ROW + pos * 8) = v[s];
 #pragma unroll
@@ -378,7 +415,9 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
         // prefetches of 4 KiB by the TMA engine, half a transform ahead: early enough to cover the HBM latency, late
         // enough not to crowd the L2
         if (tid < 32 && more) {
-          const float2 *nx = in + (size_t)(t + gridDim.x) * N + 1024 * tid + 512;
+          int tr = (t + gridDim.x) * NTR + tid / N1;
+          tr = tr < batch ? tr : batch - 1;
+          const float2 *nx = in + (size_t)tr * N + 1024 * (tid % N1) + 512;
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"(4096) : "memory");
         }
         // the second job's rows: tensor memory -> row buffers
@@ -430,7 +469,7 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
         const bool mirrored = REAL && job == 0;
         const int slot = mirrored ? ((16 - s) & 15) : s;
         const int k2 = (h != (int)mirrored) ? 31 - warp : warp;
-        const int k1 = 16 * job + slot;
+        const int k1 = LOG1 == 5 ? 16 * job + slot : slot;  // LOG1 = 4: job = transform of the unit, rows 0..15 each
         const unsigned char *p = rows + slot * G::ROW + k2 * G::K2S;
         float2 v[32];
 #pragma unroll
@@ -449,10 +488,12 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
           __syncwarp();
         }
         B2F_SMX_FFT(dft32<INV>(v));
-        float2 *o = dst + k1 + 32 * k2;
+        float2 *o = dst + (LOG1 == 5 ? 0 : (size_t)job * N) + k1 + N1 * k2;
         if constexpr (!REAL) {
+          if (LOG1 == 5 || t * NTR + job < batch) {  // (the second transform of the last unit of an odd batch)
 #pragma unroll
-          for (int k3 = 0; k3 < 32; k3++) B2F_SMX_STG(o[1024 * k3], cscale(v[k3], scale));
+            for (int k3 = 0; k3 < 32; k3++) B2F_SMX_STG(o[32 * N1 * k3], cscale(v[k3], scale));
+          }
         } else if (job == 0) {
           if (s == 0) {  // row 0 -> Z[k2][k3]
 #pragma unroll

@@ -234,3 +234,26 @@ def test_second_device_if_present(eng):
     assert eng.Clcfft(0, 1024, True).transform(a) == 0
     assert eng.Clcfft(1, 1024, True).transform(b) == 0
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 149, 297, 300])
+def test_one_sm_kernel_16384_point_complex(eng, options, batch):
+    """N = 2^14 on the one-SM kernel: two transforms per unit of work (the second parked in tensor memory while the
+    first is processed), so odd batches end in a half-empty unit and 297+ make CTAs loop. Every transform, forward and
+    inverse, against float64; then the default selection (small batches on cfft_kernel<14>) must agree to rounding."""
+    N = 16384
+    rng = np.random.default_rng(batch)
+    z = crand(rng, batch, N)
+    zz = z.astype(np.complex128)
+    got = {}
+    for forced in (1, 0):
+        options("fft_sm_min_batch", forced)
+        for fwd in (True, False):
+            p = eng.Clcfft(0, N, fwd, max_batch=batch)
+            y = z.copy()
+            assert p.transform(y.reshape(-1)) == 0
+            truth = np.fft.fft(zz, axis=1) / N if fwd else np.fft.ifft(zz, axis=1) * N
+            err = np.linalg.norm(y - truth, axis=1) / np.linalg.norm(truth, axis=1)
+            assert err.max() < 2e-6, (forced, fwd, int(err.argmax()), float(err.max()))
+            got[forced, fwd] = y
+    assert rel_l2(got[1, True], got[0, True]) < 1e-6 and rel_l2(got[1, False], got[0, False]) < 1e-6

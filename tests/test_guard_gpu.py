@@ -1,4 +1,4 @@
-"""Out-of-bounds write detection without compute-sanitizer (closed on this pool): every device-pointer entry
+"""Out-of-bounds write detection without compute-sanitizer (closed on this pool, in round 2 too): every device-pointer entry
 point is run on buffers carved out of a larger allocation whose surroundings hold a sentinel; the sentinel
 must be intact afterwards, for odd batch / channel counts that leave partially filled CTAs and tiles."""
 import numpy as np
@@ -39,7 +39,28 @@ def test_fft_device_entry_points_stay_in_bounds(eng, logn, batch):
             assert src.intact()
 
 
-@pytest.mark.parametrize("pts,nparts,channels", [(16, 3, 5), (512, 7, 3), (512, 5, 301), (1024, 4, 65), (2048, 3, 2), (8192, 2, 3)])
+@pytest.mark.parametrize("batch", [3, 149])
+def test_one_sm_fft_stays_in_bounds(eng, options, batch):
+    """The one-SM kernel (TMA-staged input, persistent CTAs): forced for a batch smaller than the grid and for one that
+    makes a single CTA take a second transform; complex both ways, real forward and inverse, in and out of place."""
+    options("fft_sm_min_batch", 1)
+    n = 32768
+    for real in (False, True):
+        for fwd in (True, False):
+            plan = eng.Clrfft(0, 2 * n, fwd, max_batch=batch) if real else eng.Clcfft(0, n, fwd, max_batch=batch)
+            assert plan.get_error() == 0
+            src, dst = Guarded(batch * n * 2), Guarded(batch * n * 2)
+            src.view.uniform_(-1, 1)
+            assert plan.transform_dev(src.view, dst.view, batch) == 0
+            torch.cuda.synchronize()
+            assert src.intact() and dst.intact()
+            assert torch.isfinite(dst.view).all() and not (dst.view == SENT).any()
+            assert plan.transform_dev(src.view, src.view, batch) == 0  # in place
+            torch.cuda.synchronize()
+            assert src.intact()
+
+
+@pytest.mark.parametrize("pts,nparts,channels", [(16, 3, 5), (512, 7, 3), (512, 5, 301), (1024, 4, 65), (2048, 3, 2), (4096, 3, 3), (8192, 2, 3)])
 def test_pconv_device_entry_points_stay_in_bounds(eng, pts, nparts, channels):
     cvs = pts * nparts + 3
     c = eng.Clpconv(0, cvs, pts, channels=channels)
