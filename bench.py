@@ -310,14 +310,15 @@ def bench_pconv_single_process(eng, devices, steps, warmup, channels_per_gpu=CHA
     conv = eng.Clpconv(0, cvs, pts, channels=channels, devices=devices)
     if conv.get_cl_err():
         raise RuntimeError("Clpconv(devices=...): " + eng.cl_error_string(conv.get_cl_err()))
-    # the same decaying-noise IRs, generated on the host in float32 (1.9 GB per GPU's worth of channels)
+    # decaying-noise IRs generated on the host in float32: one GPU's worth (1.9 GB), uploaded to every device's shard
     rng = np.random.default_rng(7000)
     env = np.exp(-6.9078 * np.arange(cvs, dtype=np.float32) / cvs)
-    ir = np.empty((channels, cvs), np.float32)
-    for c0 in range(0, channels, 64):
-        blk = rng.standard_normal((min(64, channels - c0), cvs), dtype=np.float32) * env
+    ir = np.empty((channels_per_gpu, cvs), np.float32)
+    for c0 in range(0, channels_per_gpu, 64):
+        blk = rng.standard_normal((min(64, channels_per_gpu - c0), cvs), dtype=np.float32) * env
         ir[c0:c0 + blk.shape[0]] = blk / np.linalg.norm(blk, axis=1, keepdims=True)
-    assert conv.push_ir(ir) == 0
+    for g in range(n):
+        assert conv.push_ir_shard(g, ir) == 0
     del ir
     hx = torch.empty(4, channels, pts).pin_memory()
     hx.uniform_(-1, 1)

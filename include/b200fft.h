@@ -184,6 +184,8 @@ int b2f_pconv_multi_destroy(b2f_pconv_multi *h);
 int b2f_pconv_multi_nparts(const b2f_pconv_multi *h);
 int b2f_pconv_multi_reset(b2f_pconv_multi *h);
 int b2f_pconv_multi_push_ir_host(b2f_pconv_multi *h, const float *ir, size_t ir_stride);
+/* the same for the channels of devices[g] only (ir: that shard's IRs), e.g. to upload a large set shard by shard */
+int b2f_pconv_multi_push_ir_shard_host(b2f_pconv_multi *h, int g, const float *ir, size_t ir_stride);
 int b2f_pconv_multi_process_host(b2f_pconv_multi *h, float *out, const float *in);
 int b2f_pconv_multi_process_tv_host(b2f_pconv_multi *h, float *out, const float *in1, const float *in2);
 typedef struct b2f_dconv_multi b2f_dconv_multi;

@@ -207,6 +207,7 @@ class Clpconv:
         self._errs, self._udata = errs, uData
         self._h = C.c_void_p()
         self._multi = devices is not None
+        self._devices = list(devices) if devices is not None else [device]
         L = lib()
         if self._multi:
             arr, n = _devlist(devices)
@@ -245,6 +246,18 @@ class Clpconv:
             return self._err
         self._err = self._f[0](self._h, ir.ctypes.data, stride)
         return self._err
+
+    def push_ir_shard(self, g: int, ir: np.ndarray) -> int:
+        """devices=[...] only: the IRs of the channels that live on devices[g] (contiguous range g of len(devices))."""
+        if not self._multi:
+            raise TypeError("push_ir_shard needs devices=[...]")
+        ir = _host(ir, np.float32, "ir")
+        n = len(self._devices)
+        count = (g + 1) * self.channels // n - g * self.channels // n
+        stride = ir.shape[-1] if ir.ndim > 1 else ir.size // count
+        if stride < self.nparts * self.pts or ir.size < (count - 1) * stride + self.nparts * self.pts:
+            return INVALID_VALUE
+        return lib().b2f_pconv_multi_push_ir_shard_host(self._h, g, ir.ctypes.data, stride)
 
     def convolution(self, output: np.ndarray, input1: np.ndarray, input2: np.ndarray | None = None) -> int:
         out = _host(output, np.float32, "output")

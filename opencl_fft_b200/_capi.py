@@ -53,6 +53,7 @@ SYMBOLS = {
     "b2f_pconv_multi_nparts": (_i, [_vp]),
     "b2f_pconv_multi_reset": (_i, [_vp]),
     "b2f_pconv_multi_push_ir_host": (_i, [_vp, _vp, _sz]),
+    "b2f_pconv_multi_push_ir_shard_host": (_i, [_vp, _i, _vp, _sz]),
     "b2f_pconv_multi_process_host": (_i, [_vp, _vp, _vp]),
     "b2f_pconv_multi_process_tv_host": (_i, [_vp, _vp, _vp, _vp]),
     "b2f_dconv_multi_create": (_i, [_pp, C.POINTER(_i), _i, _i, _i, _i, _i]),

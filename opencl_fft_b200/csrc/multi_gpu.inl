@@ -142,6 +142,12 @@ extern "C" int b2f_pconv_multi_push_ir_host(b2f_pconv_multi *h, const float *ir,
     return b2f_pconv_push_ir_host(h->sub[g], ir + (size_t)h->sh.begin(g, h->sh.total) * ir_stride, ir_stride);
   });
 }
+// one device's shard only: `ir` holds the IRs of channels [g*channels/ndev, (g+1)*channels/ndev), `ir_stride` apart
+extern "C" int b2f_pconv_multi_push_ir_shard_host(b2f_pconv_multi *h, int g, const float *ir, size_t ir_stride) {
+  if (!h || !ir || g < 0 || g >= h->sh.ndev) return B2F_ERR_INVALID_VALUE;
+  h->sh.workers[g]->post([&] { return b2f_pconv_push_ir_host(h->sub[g], ir, ir_stride); });
+  return h->sh.workers[g]->wait();
+}
 extern "C" int b2f_pconv_multi_process_host(b2f_pconv_multi *h, float *out, const float *in) {
   if (!h || !out || !in) return B2F_ERR_INVALID_VALUE;
   return h->sh.fan_out([&](int g) {

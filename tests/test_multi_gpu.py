@@ -73,6 +73,27 @@ def test_dconv_and_fft_multi_equal_single_device(eng):
         assert np.array_equal(got[0], fwant[0]) and np.array_equal(got[1], fwant[1]), devs
 
 
+def test_push_ir_shard_by_shard(eng):
+    pts, nparts, channels = 64, 3, 10
+    cvs = pts * nparts
+    rng = np.random.default_rng(8)
+    ir = rng.standard_normal((channels, cvs)).astype(np.float32)
+    x = rng.uniform(-1, 1, (channels, pts)).astype(np.float32)
+    for devs in _devsets(eng):
+        a = eng.Clpconv(0, cvs, pts, channels=channels, devices=devs)
+        b = eng.Clpconv(0, cvs, pts, channels=channels, devices=devs)
+        assert a.push_ir(ir) == 0
+        n = len(devs)
+        for g in range(n):
+            lo, hi = g * channels // n, (g + 1) * channels // n
+            assert b.push_ir_shard(g, ir[lo:hi]) == 0
+        assert b.push_ir_shard(n, ir) == 2 and b.push_ir_shard(0, ir[:0]) == 2
+        ya, yb = np.zeros_like(x), np.zeros_like(x)
+        for _ in range(nparts + 1):
+            assert a.convolution(ya, x) == 0 and b.convolution(yb, x) == 0
+        assert np.array_equal(ya, yb)
+
+
 def test_multi_argument_errors(eng):
     assert eng.Clpconv(0, 4096, 512, channels=4, devices=[0, 0], uData=1).get_cl_err() == 2  # the same device twice
     assert eng.Clpconv(0, 4096, 512, channels=1, devices=[0, 99], uData=1).get_cl_err() == 2  # fewer channels than devices
