@@ -52,13 +52,8 @@
 namespace b2f {
 
 // ---- radix-32 butterfly: natural order in, natural order out ------------------------------------------------------
-// `drain(q)`, q = 0..3, is called between the stages: the deferred global stores of an earlier pass (four values per
-// call, out of tensor memory) are spread through the butterflies instead of being issued in one burst (see Drain).
-struct NoDrain {
-  __device__ __forceinline__ void operator()(int) const {}
-};
-template <bool INV, class D = NoDrain>
-__device__ __forceinline__ void dft32(float2 (&v)[32], const D &drain = D()) {
+template <bool INV>
+__device__ __forceinline__ void dft32(float2 (&v)[32]) {
   constexpr float kC[16] = {1.f,
                             0.98078528040323043f,
                             0.92387953251128674f,
@@ -97,11 +92,8 @@ __device__ __forceinline__ void dft32(float2 (&v)[32], const D &drain = D()) {
     e[i] = v[2 * i];
     o[i] = v[2 * i + 1];
   }
-  drain(0);
   dft16<INV>(e);
-  drain(1);
   dft16<INV>(o);
-  drain(2);
 #pragma unroll
   for (int i = 1; i < 16; i++) o[i] = (i == 8) ? cquarter<INV>(o[i]) : cmulc<INV>(o[i], kC[i], kS[i]);
 #pragma unroll
@@ -109,7 +101,6 @@ __device__ __forceinline__ void dft32(float2 (&v)[32], const D &drain = D()) {
     v[i] = cadd(e[i], o[i]);
     v[i + 16] = csub(e[i], o[i]);
   }
-  drain(3);
 }
 
 // v[m] *= W^m for m = 1..31, given W^1, W^2, W^4, W^8, W^16 (base[b] = W^(2^b)): the other 26 powers are products
@@ -128,20 +119,16 @@ __device__ __forceinline__ void tw_tree(float2 (&v)[32], float2 p, const float2 
   }
 }
 // two independent 16-point butterflies on v[0..15] and v[16..31] (N = 2^14: two transforms per unit)
-template <bool INV, class D = NoDrain>
-__device__ __forceinline__ void dft16x2(float2 (&v)[32], const D &drain = D()) {
+template <bool INV>
+__device__ __forceinline__ void dft16x2(float2 (&v)[32]) {
   float2 a[16], b[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     a[i] = v[i];
     b[i] = v[16 + i];
   }
-  drain(0);
   dft16<INV>(a);
-  drain(1);
-  drain(2);
   dft16<INV>(b);
-  drain(3);
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     v[i] = a[i];
@@ -190,39 +177,7 @@ __device__ __forceinline__ void wait_ld8(float2 (&v)[8]) {
                  "+f"(v[3].y), "+f"(v[4].x), "+f"(v[4].y), "+f"(v[5].x), "+f"(v[5].y), "+f"(v[6].x), "+f"(v[6].y),
                  "+f"(v[7].x), "+f"(v[7].y)::"memory");
 }
-// four complex values <-> eight columns
-__device__ __forceinline__ void ld4(uint32_t taddr, float2 (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y)
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void wait_ld4(float2 (&v)[4]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[2].x), "+f"(v[2].y), "+f"(v[3].x), "+f"(v[3].y)::"memory");
-}
 }  // namespace tmem
-
-// Deferred stores. A pass B does not store its 32 results per thread: it parks them in the thread's tensor-memory
-// columns, and later butterflies -- of the same unit or of the next one -- call step(q) between their stages, which
-// fetches four parked values and stores them. The SM's store path takes ~45 B/clk; 256 KiB issued in one burst at the end
-// of a pass stalls every warp of the CTA on a full store queue with nothing else to run (ncu: `lg` / `mio` throttle on
-// the STGs, a quarter of the kernel's time), whereas 16 stores per thread spread over a butterfly drain behind its
-// arithmetic. `on` is uniform over the CTA.
-struct Drain {
-  uint32_t tcol;  // tensor-memory address of the first of this phase's 16 values (value i at column 2 i)
-  float2 *ptr;    // where that value goes
-  int stride;     // float2 elements between consecutive values
-  bool on;
-  __device__ __forceinline__ void operator()(int q) const {
-    if (!on) return;
-    float2 d[4];
-    tmem::ld4(tcol + 8 * q, d);
-    tmem::wait_ld4(d);
-#pragma unroll
-    for (int i = 0; i < 4; i++) B2F_SMX_STG(ptr[(size_t)((4 * q + i) * stride)], d[i]);
-  }
-};
 
 // ---- geometry ---------------------------------------------------------------------------------------------------------
 struct SmGeom {
