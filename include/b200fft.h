@@ -67,7 +67,8 @@ const char *b2f_version(void);
  *   pconv_tma         -1     partitioned-convolution MAC feed: -1 measured choice, 0 registers, 1 TMA
  *   pconv_cluster     0      cluster split of the partitions: 0 measured choice, else 1 | 2 | 4 | 8
  *                            (anything else, or more than nparts: create fails with INVALID_VALUE)
- *   pconv_pipeline    1      two-stream host call for >= 128 channels
+ *   pconv_pipeline    1      two-stream host calls: partitioned convolution with >= 128 channels (halves of the
+ *                            channels), FFT batches above 1 MB (eight chunks of the batch)
  *   zerocopy_max      65536  host calls moving at most this many bytes run on pinned buffers directly
  *   graph             1      CUDA graph replay for the multi-launch host paths (pts >= 8192)
  *   verbose           0

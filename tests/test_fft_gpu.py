@@ -257,3 +257,29 @@ def test_one_sm_kernel_16384_point_complex(eng, options, batch):
             assert err.max() < 2e-6, (forced, fwd, int(err.argmax()), float(err.max()))
             got[forced, fwd] = y
     assert rel_l2(got[1, True], got[0, True]) < 1e-6 and rel_l2(got[1, False], got[0, False]) < 1e-6
+
+
+@pytest.mark.parametrize("size,batch", [(4096, 1031), (65536, 800)])
+def test_pipelined_host_call_equals_single_stream(eng, options, size, batch):
+    """Host calls above 1 MB cut the batch into chunks alternating between two streams (upload, transform and download
+    of different chunks overlap). Same bits as the single-stream call, real and complex, odd batch included; 65536 x 800
+    puts 100 transforms per chunk on the one-SM kernel."""
+    rng = np.random.default_rng(size)
+    r = rng.uniform(-1, 1, (batch, size)).astype(np.float32)
+    z = crand(rng, batch // 2, size // 2)
+    res = {}
+    for pipe in (1, 0):
+        options("pconv_pipeline", pipe)
+        f = eng.Clrfft(0, size, True, max_batch=batch)
+        c = np.zeros((batch, size // 2), np.complex64)
+        assert f.transform(c.reshape(-1), r.reshape(-1).copy()) == 0
+        i = eng.Clrfft(0, size, False, max_batch=batch)
+        back = np.zeros((batch, size), np.float32)
+        assert i.transform(c.copy().reshape(-1), back.reshape(-1)) == 0
+        p = eng.Clcfft(0, size // 2, True, max_batch=batch // 2)
+        y = z.copy()
+        assert p.transform(y.reshape(-1)) == 0
+        res[pipe] = (c, back, y)
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert np.abs(res[1][1] - r).max() < 2e-5
