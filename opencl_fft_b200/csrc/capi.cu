@@ -251,26 +251,52 @@ static int set_smem(K kernel, int bytes) {
 template <int LOGN>
 static int launch_cfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, int batch, float scale,
                          cudaStream_t st) {
-  using B = BatchGeom<LOGN>;
-  const int grid = (batch + B::TPB - 1) / B::TPB;
-  if (inv) {
-    int rc = set_smem(cfft_kernel<LOGN, true>, B::SMEM_BYTES);
-    if (rc) return rc;
-    cfft_kernel<LOGN, true><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, batch, scale);
+  if constexpr (ThreadGeom<LOGN>::OK) {  // one thread per transform (N = 2, 4, 32)
+    using G = ThreadGeom<LOGN>;
+    const int grid = (batch + G::PER_CTA - 1) / G::PER_CTA;
+    if (inv) {
+      int rc = set_smem(fft_thread_kernel<LOGN, kThreadComplex, true>, G::SMEM_BYTES);
+      if (rc) return rc;
+      fft_thread_kernel<LOGN, kThreadComplex, true><<<grid, G::THREADS, G::SMEM_BYTES, st>>>((const float4 *)in, (float4 *)out, nullptr, batch, scale);
+    } else {
+      int rc = set_smem(fft_thread_kernel<LOGN, kThreadComplex, false>, G::SMEM_BYTES);
+      if (rc) return rc;
+      fft_thread_kernel<LOGN, kThreadComplex, false><<<grid, G::THREADS, G::SMEM_BYTES, st>>>((const float4 *)in, (float4 *)out, nullptr, batch, scale);
+    }
   } else {
-    int rc = set_smem(cfft_kernel<LOGN, false>, B::SMEM_BYTES);
-    if (rc) return rc;
-    cfft_kernel<LOGN, false><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, batch, scale);
+    using B = BatchGeom<LOGN>;
+    const int grid = (batch + B::TPB - 1) / B::TPB;
+    if (inv) {
+      int rc = set_smem(cfft_kernel<LOGN, true>, B::SMEM_BYTES);
+      if (rc) return rc;
+      cfft_kernel<LOGN, true><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, batch, scale);
+    } else {
+      int rc = set_smem(cfft_kernel<LOGN, false>, B::SMEM_BYTES);
+      if (rc) return rc;
+      cfft_kernel<LOGN, false><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, batch, scale);
+    }
   }
   CK(cudaGetLastError());
   return B2F_OK;
 }
 template <int LOGN>
-static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *w2, const float2 *hw,
-                         int batch, float fwd_scale, cudaStream_t st) {
-  using B = BatchGeom<LOGN>;
-  const int grid = (batch + B::TPB - 1) / B::TPB;
-  if constexpr (RegSplitGeom<LOGN>::OK) {
+static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *hw, int batch,
+                         float fwd_scale, cudaStream_t st) {
+  if constexpr (ThreadGeom<LOGN>::OK) {  // one thread per transform, split / unsplit in registers (N = 2, 4, 32)
+    using G = ThreadGeom<LOGN>;
+    const int grid = (batch + G::PER_CTA - 1) / G::PER_CTA;
+    if (inv) {
+      int rc = set_smem(fft_thread_kernel<LOGN, kThreadRealInv, true>, G::SMEM_BYTES);
+      if (rc) return rc;
+      fft_thread_kernel<LOGN, kThreadRealInv, true><<<grid, G::THREADS, G::SMEM_BYTES, st>>>((const float4 *)in, (float4 *)out, hw, batch, 1.0f);
+    } else {
+      int rc = set_smem(fft_thread_kernel<LOGN, kThreadRealFwd, false>, G::SMEM_BYTES);
+      if (rc) return rc;
+      fft_thread_kernel<LOGN, kThreadRealFwd, false><<<grid, G::THREADS, G::SMEM_BYTES, st>>>((const float4 *)in, (float4 *)out, hw, batch, fwd_scale);
+    }
+  } else if constexpr (RegSplitGeom<LOGN>::OK) {
+    using B = BatchGeom<LOGN>;
+    const int grid = (batch + B::TPB - 1) / B::TPB;
     // register-level split / unsplit (fft_kernels.cuh, second half)
     if (inv) {
       int rc = set_smem(rfft_inv_reg_kernel<LOGN>, B::SMEM_BYTES);
@@ -281,18 +307,8 @@ static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *
       if (rc) return rc;
       rfft_fwd_reg_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, hw, batch, fwd_scale);
     }
-    CK(cudaGetLastError());
-    return B2F_OK;
-  }
-  using BR = BatchGeom<LOGN, true>;  // generic real kernels (N < 128)
-  if (inv) {
-    int rc = set_smem(rfft_inv_kernel<LOGN>, BR::SMEM_BYTES);
-    if (rc) return rc;
-    rfft_inv_kernel<LOGN><<<grid, BR::THREADS, BR::SMEM_BYTES, st>>>(in, out, tw, w2, batch);
   } else {
-    int rc = set_smem(rfft_fwd_kernel<LOGN>, BR::SMEM_BYTES);
-    if (rc) return rc;
-    rfft_fwd_kernel<LOGN><<<grid, BR::THREADS, BR::SMEM_BYTES, st>>>(in, out, tw, w2, batch, fwd_scale);
+    static_assert(LOGN < 0, "every size has a real-transform kernel");
   }
   CK(cudaGetLastError());
   return B2F_OK;
@@ -323,9 +339,9 @@ static int launch_cfft(int logn, bool inv, const float2 *in, float2 *out, const 
   B2F_DISPATCH_LOGN(logn, CALL)
 #undef CALL
 }
-static int launch_rfft(int logn, bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *w2,
-                       const float2 *hw, int batch, float fwd_scale, cudaStream_t st) {
-#define CALL(L) launch_rfft_t<L>(inv, in, out, tw, w2, hw, batch, fwd_scale, st)
+static int launch_rfft(int logn, bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *hw, int batch,
+                       float fwd_scale, cudaStream_t st) {
+#define CALL(L) launch_rfft_t<L>(inv, in, out, tw, hw, batch, fwd_scale, st)
   B2F_DISPATCH_LOGN(logn, CALL)
 #undef CALL
 }
@@ -665,7 +681,7 @@ struct FftPlanCore {
       return fwd ? sm.run<false, kSmRealFwd>(in, out, d_hw, batch, fwd_scale(), st)
                  : sm.run<true, kSmRealInv>(in, out, d_hw, batch, 1.0f, st);
     if (is_large()) return large.run_real(!fwd, in, out, d_w2, d_hw, batch, fwd_scale(), st);
-    return launch_rfft(logn, !fwd, in, out, d_tw, d_w2, d_hw, batch, fwd_scale(), st);
+    return launch_rfft(logn, !fwd, in, out, d_tw, d_hw, batch, fwd_scale(), st);
   }
 };
 

@@ -166,12 +166,64 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
     v[i + 8] = csub(e[i], o[i]);
   }
 }
+// radix 32 (the one-SM kernel of fft_sm.cuh and the one-thread-per-transform kernel of fft_kernels.cuh)
+template <bool INV>
+__device__ __forceinline__ void dft32(float2 (&v)[32]) {
+  constexpr float kC[16] = {1.f,
+                            0.98078528040323043f,
+                            0.92387953251128674f,
+                            0.83146961230254524f,
+                            0.70710678118654757f,
+                            0.55557023301960229f,
+                            0.38268343236508984f,
+                            0.19509032201612833f,
+                            0.f,
+                            -0.19509032201612833f,
+                            -0.38268343236508984f,
+                            -0.55557023301960229f,
+                            -0.70710678118654757f,
+                            -0.83146961230254524f,
+                            -0.92387953251128674f,
+                            -0.98078528040323043f};
+  constexpr float kS[16] = {0.f,
+                            0.19509032201612825f,
+                            0.38268343236508978f,
+                            0.55557023301960218f,
+                            0.70710678118654757f,
+                            0.83146961230254524f,
+                            0.92387953251128674f,
+                            0.98078528040323043f,
+                            1.f,
+                            0.98078528040323043f,
+                            0.92387953251128674f,
+                            0.83146961230254524f,
+                            0.70710678118654757f,
+                            0.55557023301960218f,
+                            0.38268343236508978f,
+                            0.19509032201612825f};
+  float2 e[16], o[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    e[i] = v[2 * i];
+    o[i] = v[2 * i + 1];
+  }
+  dft16<INV>(e);
+  dft16<INV>(o);
+#pragma unroll
+  for (int i = 1; i < 16; i++) o[i] = (i == 8) ? cquarter<INV>(o[i]) : cmulc<INV>(o[i], kC[i], kS[i]);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    v[i] = cadd(e[i], o[i]);
+    v[i + 16] = csub(e[i], o[i]);
+  }
+}
 template <int R, bool INV>
 __device__ __forceinline__ void dftR(float2 (&v)[R]) {
   if constexpr (R == 2) dft2<INV>(v[0], v[1]);
   if constexpr (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
   if constexpr (R == 8) dft8<INV>(v);
   if constexpr (R == 16) dft16<INV>(v);
+  if constexpr (R == 32) dft32<INV>(v);
 }
 
 // ---- geometry of one plan ----------------------------------------------------------------------

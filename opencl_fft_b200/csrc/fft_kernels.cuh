@@ -1,9 +1,12 @@
 // fft_kernels.cuh -- batched C2C / R2C / C2R kernels for transforms that fit one CTA (N <= 16384).
 //
 // Replaces (reference, relative to /root/reference):
-//   cfft_kernel      <- Clcfft::transform's reorder + log2(N) `fft` launches, cl_fft.cpp:138-161, 24-41
-//   rfft_fwd_kernel  <- Clrfft forward: the above + `conv`, cl_fft.cpp:272-282, 178-191
-//   rfft_inv_kernel  <- Clrfft inverse: `iconv` + the above, cl_fft.cpp:283-294, 192-205
+//   cfft_kernel (N >= 64), fft_thread_kernel<kThreadComplex> (N <= 32)
+//                      <- Clcfft::transform's reorder + log2(N) `fft` launches, cl_fft.cpp:138-161, 24-41
+//   rfft_fwd_reg_kernel, fft_thread_kernel<kThreadRealFwd>
+//                      <- Clrfft forward: the above + `conv`, cl_fft.cpp:272-282, 178-191
+//   rfft_inv_reg_kernel, fft_thread_kernel<kThreadRealInv>
+//                      <- Clrfft inverse: `iconv` + the above, cl_fft.cpp:283-294, 192-205
 // Each transform makes exactly one trip through HBM: 8N bytes in, 8N bytes out.
 #pragma once
 
@@ -14,38 +17,17 @@ namespace b2f {
 // threads per CTA we aim for when several small transforms share a CTA
 constexpr int kTargetThreads = 256;
 
-// REALK: geometry of the generic real-transform kernels (same as the complex ones; kept apart for re-measurement)
-template <int LOGN, bool REALK = false>
+// N >= 64 (N <= 32: one thread per transform, ThreadGeom at the end of this file)
+template <int LOGN>
 struct BatchGeom {
   using G = FftGeom<LOGN>;
   static constexpr int T = G::T;
   static constexpr int TPB = (T >= kTargetThreads) ? 1 : (kTargetThreads / T);  // transforms per CTA
   static constexpr int THREADS = T * TPB;
-  // Transforms of N <= 32 points are carried by one or two threads, whose own accesses to global memory would be
-  // 128-byte strides across a warp (measured: 28 % / 48 % of the HBM peak at N = 16 / 32). The CTA's TPB
-  // transforms are one contiguous block of memory instead: it is copied in and out cooperatively (coalesced),
-  // straight into / out of the engine's per-transform work rows, which the transform then uses in place.
-  static constexpr bool STAGED = LOGN <= 5;  // (N = 64, generic real kernels: staged 56 %, direct 71 % of the HBM peak)
-  static constexpr int ROW = STAGED ? (G::SMEM | 1) : G::SMEM;  // odd row stride: one-thread-per-row accesses conflict-free
+  static constexpr int ROW = G::SMEM;
   static constexpr int SMEM_BYTES = TPB * ROW * (int)sizeof(float2);
   static constexpr int MIN_BLOCKS = 1024 / THREADS;  // caps registers at 64/thread: 32 resident warps per SM
 };
-
-// cooperative, coalesced copy of the CTA's block of transforms between global memory and the work rows
-template <int LOGN, bool TO_SMEM, bool REALK = false>
-__device__ __forceinline__ void stage_copy(const float2 *gin, float2 *gout, float2 *rows, long long total) {
-  using B = BatchGeom<LOGN, REALK>;
-  constexpr int N = 1 << LOGN;
-  const long long base = (long long)blockIdx.x * B::TPB * N;
-  const int n = (int)(total - base < (long long)B::TPB * N ? total - base : (long long)B::TPB * N);
-  for (int i = threadIdx.x; i < n; i += B::THREADS) {
-    float2 *cell = rows + (i >> LOGN) * B::ROW + pad_idx(i & (N - 1));
-    if (TO_SMEM)
-      *cell = gin[base + i];
-    else
-      gout[base + i] = *cell;
-  }
-}
 
 // ---- complex to complex ------------------------------------------------------------------------
 // in/out: [batch][N] float2, may alias (each CTA gathers its whole transform before it scatters).
@@ -62,16 +44,6 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   const float2 *src = in + (active ? b : 0) * N;
   float2 *dst = out + (active ? b : 0) * N;
   float2 *sm = smem + lt * BatchGeom<LOGN>::ROW;
-  if constexpr (B::STAGED) {
-    stage_copy<LOGN, true>(in, nullptr, smem, (long long)batch * N);
-    __syncthreads();
-    auto load = [&](int idx, int) { return sm[pad_idx(idx)]; };
-    auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = cscale(v, scale); };
-    fft_run<LOGN, INV, true, true>(load, store, sm, tw, t, CtaSync());
-    __syncthreads();
-    stage_copy<LOGN, false>(nullptr, out, smem, (long long)batch * N);
-    return;
-  }
   auto load = [&](int idx, int) { return active ? src[idx] : make_float2(0.f, 0.f); };
   auto store = [&](int idx, float2 v, int) {
     if (active) dst[idx] = cscale(v, scale);
@@ -79,122 +51,14 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   fft_run<LOGN, INV>(load, store, sm, tw, t, CtaSync());
 }
 
-// ---- real to complex (forward) -------------------------------------------------------------------
-// in: [batch][2N] float (read as N packed float2), out: [batch][N] float2, may alias.
-// Output convention of the reference: element 0 = (DC, Nyquist)/size packed, element k =
-// 2 X[k]/size, element N/2 left as the plain FFT value (the reference's split never visits it, Q3).
-template <int LOGN>
-__global__ void __launch_bounds__(BatchGeom<LOGN, true>::THREADS, BatchGeom<LOGN, true>::MIN_BLOCKS)
-    rfft_fwd_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ w2,
-                    int batch, float scale) {
-  using B = BatchGeom<LOGN, true>;
-  constexpr int N = 1 << LOGN;
-  extern __shared__ float2 smem[];
-  const int lt = threadIdx.x / B::T, t = threadIdx.x % B::T;
-  const long long b = (long long)blockIdx.x * B::TPB + lt;
-  const bool active = b < batch;
-  const float2 *src = in + (active ? b : 0) * N;
-  float2 *dst = out + (active ? b : 0) * N;
-  float2 *sm = smem + lt * B::ROW;
-  if constexpr (B::STAGED) {  // coalesced copy-in; the transform then works in its row, the split rewrites it in place
-    stage_copy<LOGN, true, true>(in, nullptr, smem, (long long)batch * N);
-    __syncthreads();
-  }
-  auto load = [&](int idx, int) {
-    if constexpr (B::STAGED) return sm[pad_idx(idx)];
-    return active ? src[idx] : make_float2(0.f, 0.f);
-  };
-  auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = cscale(v, scale); };
-  fft_run<LOGN, false, true, B::STAGED>(load, store, sm, tw, t, CtaSync());
-  __syncthreads();
-  auto put = [&](int i, float2 v) {
-    if constexpr (B::STAGED)
-      sm[pad_idx(i)] = v;
-    else
-      dst[i] = v;
-  };
-  if (active) {
-    // split: pairs (i, N-i), i in [1, N/2); elements 0 and N/2 handled apart
-    for (int i = t; i <= N / 2; i += B::T) {
-      if (i == 0) {
-        put(0, rfft_dc<false>(sm[pad_idx(0)]));
-      } else if (i == N / 2) {
-        put(i, sm[pad_idx(i)]);
-      } else {
-        float2 ci = sm[pad_idx(i)], cj = sm[pad_idx(N - i)];
-        rfft_pair<false>(ci, cj, __ldg(&w2[i]));
-        put(i, ci);
-        put(N - i, cj);
-      }
-    }
-  }
-  if constexpr (B::STAGED) {
-    __syncthreads();
-    stage_copy<LOGN, false, true>(nullptr, out, smem, (long long)batch * N);
-  }
-}
-
-// ---- complex to real (inverse) -------------------------------------------------------------------
-// in: [batch][N] float2 in the layout rfft_fwd_kernel writes, out: [batch][2N] float, may alias.
-template <int LOGN>
-__global__ void __launch_bounds__(BatchGeom<LOGN, true>::THREADS, BatchGeom<LOGN, true>::MIN_BLOCKS)
-    rfft_inv_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ w2,
-                    int batch) {
-  using B = BatchGeom<LOGN, true>;
-  constexpr int N = 1 << LOGN;
-  extern __shared__ float2 smem[];
-  const int lt = threadIdx.x / B::T, t = threadIdx.x % B::T;
-  const long long b = (long long)blockIdx.x * B::TPB + lt;
-  const bool active = b < batch;
-  const float2 *src = in + (active ? b : 0) * N;
-  float2 *dst = out + (active ? b : 0) * N;
-  float2 *sm = smem + lt * B::ROW;
-  if constexpr (B::STAGED) {  // coalesced copy-in; unsplit and transform in place in the row, coalesced copy-out
-    stage_copy<LOGN, true, true>(in, nullptr, smem, (long long)batch * N);
-    __syncthreads();
-  }
-  auto get = [&](int i) {
-    if constexpr (B::STAGED) return sm[pad_idx(i)];
-    return src[i];
-  };
-  if (active) {
-    for (int i = t; i <= N / 2; i += B::T) {
-      if (i == 0) {
-        sm[pad_idx(0)] = rfft_dc<true>(get(0));
-      } else if (i == N / 2) {
-        sm[pad_idx(i)] = get(i);
-      } else {
-        float2 ci = get(i), cj = get(N - i);
-        rfft_pair<true>(ci, cj, __ldg(&w2[i]));
-        sm[pad_idx(i)] = ci;
-        sm[pad_idx(N - i)] = cj;
-      }
-    }
-  }
-  __syncthreads();
-  auto load = [&](int idx, int) { return sm[pad_idx(idx)]; };
-  auto store = [&](int idx, float2 v, int) {
-    if constexpr (B::STAGED)
-      sm[pad_idx(idx)] = v;
-    else if (active)
-      dst[idx] = v;
-  };
-  fft_run<LOGN, true, B::STAGED, true>(load, store, sm, tw, t, CtaSync());
-  if constexpr (B::STAGED) {
-    __syncthreads();
-    stage_copy<LOGN, false, true>(nullptr, out, smem, (long long)batch * N);
-  }
-}
-
-
 // =====================================================================================================
 // Register-level real transforms for N >= 64 (schedules whose first and last passes leave every thread
 // with the E = 16 (8 at N = 64) values X[t + m*T], m = 0..E-1, T = N/E; written below for E = 16). The pair partner of element (t, m) is element
 // (T - t, 15 - m) [(0, 16 - m) for t = 0], so the split / unsplit needs ONE partner thread: the two swap
 // half of their values through a small shared-memory staging area, each evaluates its 8 pairs once (the inverse
 // reads the partner's inputs from global memory instead and only hands the results over).
-// Against the generic kernels above this drops a full shared-memory round trip and halves the split
-// arithmetic: 0.5, the 1/N scaling and the quarter turn are folded into the table
+// Against a split pass over the finished transform in shared memory this drops a full shared-memory round trip
+// and halves the split arithmetic: 0.5, the 1/N scaling and the quarter turn are folded into the table
 //   hw[i] = 0.5 * scale * i * w2[i]  (forward)      hw[i] = conj(0.5 * i * w2[i])  (inverse)
 // so that   out_i = hs*S + hw*D,  out_j = conj(hs*S - hw*D),  S = A + conj(B), D = conj(B) - A,
 // the same algebra as the reference's conv/iconv kernels (cl_fft.cpp:178-205), 12 instructions per pair.
@@ -319,6 +183,145 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
     if (active) __stcs(dst + idx, v);
   };
   fft_run<LOGN, true>(load, store, sm, tw, t, CtaSync());
+}
+
+// =====================================================================================================
+// One thread, one transform: N <= 32. The transform AND the real split / unsplit (cl_fft.cpp:178-205; the pair
+// partner N - i sits in the same thread) run in registers; nothing but the coalescing copy touches shared memory.
+// N = 2 / 4: a transform is one / two 16-byte words, read and written straight from global memory, four transforms
+// per thread so that a CTA moves 16-32 KiB. N = 8, 16, 32: the CTA's transforms are one contiguous block, copied in
+// and out with 128-bit accesses into rows of N/2 + 1 float4 (an odd stride: conflict-free for the copy and for the
+// one-thread-per-row 128-bit accesses alike), and a thread holds its row in up to 64 registers.
+// These replaced multi-thread schedules through the generic engine ({8, 4} at N = 32: four threads and a shared-
+// memory exchange per transform) and 4 KiB CTAs at N = 2. Measured, fraction of the HBM copy peak, c2c / r2c / c2r:
+//   N = 2:  0.52 / 0.42 / 0.43 -> 1.02 / 1.02 / 1.02      N = 4:  0.86 / 0.71 / 0.72 -> 1.01 / 1.02 / 1.01
+//   N = 8:  1.00 / 0.85 / 0.86 -> 0.99 / 0.99 / 0.99      N = 16: 1.04 / 0.97 / 0.97 -> 1.04 / 1.03 / 1.03
+//   N = 32: 0.75 / 0.57 / 0.58 -> 1.01 / 1.01 / 0.99
+// (N = 8 wants many small CTAs: 128 threads x 8 per SM 0.99, 256 x 4 0.95, 512 x 2 0.87, unstaged 0.94.)
+// =====================================================================================================
+template <int LOGN>
+struct ThreadGeom {
+  static constexpr int N = 1 << LOGN, V = N / 2;  // V: float4 words per transform
+  static constexpr bool OK = LOGN <= 5;
+  static constexpr bool STAGED = LOGN >= 3;  // through shared memory (N >= 8)
+  static constexpr int THREADS = (LOGN == 5 || LOGN == 3) ? 128 : 256;
+  static constexpr int MIN_BLOCKS = LOGN == 3 ? 8 : 4;
+  static constexpr int ITER = 4;       // transforms per thread (direct kernels)
+  static constexpr int ROW4 = V + 1;   // row stride, float4 units
+  static constexpr int SMEM_BYTES = STAGED ? THREADS * ROW4 * 16 : 0;
+  static constexpr int PER_CTA = STAGED ? THREADS : THREADS * ITER;  // transforms per CTA
+};
+enum { kThreadComplex = 0, kThreadRealFwd = 1, kThreadRealInv = 2 };
+
+// v: the N points of one transform. hw: folded split table of the plan (forward: scale folded in), see below.
+template <int LOGN, int KIND, bool INV>
+__device__ __forceinline__ void thread_transform(float2 (&v)[1 << LOGN], const float2 *__restrict__ hw, float scale) {
+  constexpr int N = 1 << LOGN;
+  if constexpr (KIND == kThreadRealInv) {  // unsplit first (cl_fft.cpp:192-205); element N/2 passes through (Q3)
+    v[0] = rfft_dc<true>(v[0]);
+#pragma unroll
+    for (int i = 1; i < N / 2; i++) rfft_pair_folded<true>(v[i], v[N - i], __ldg(&hw[i]), 0.5f);
+  }
+  dftR<N, INV>(v);
+  if constexpr (KIND == kThreadComplex) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = cscale(v[i], scale);
+  }
+  if constexpr (KIND == kThreadRealFwd) {  // split (cl_fft.cpp:178-191): packed (DC, Nyquist), bin N/2 only scaled
+    const float hs = 0.5f * scale;
+    v[0] = make_float2((v[0].x + v[0].y) * hs, (v[0].x - v[0].y) * hs);
+    v[N / 2] = cscale(v[N / 2], scale);
+#pragma unroll
+    for (int i = 1; i < N / 2; i++) rfft_pair_folded<false>(v[i], v[N - i], __ldg(&hw[i]), hs);
+  }
+}
+
+// in/out: [batch][N] float2 (real transforms: the packed layouts of rfft_fwd_kernel / rfft_inv_kernel), may alias:
+// a CTA has read everything it owns before it writes.
+template <int LOGN, int KIND, bool INV>
+__global__ void __launch_bounds__(ThreadGeom<LOGN>::THREADS, ThreadGeom<LOGN>::MIN_BLOCKS)
+    fft_thread_kernel(const float4 *in, float4 *out, const float2 *__restrict__ hw, long long batch, float scale) {
+  using G = ThreadGeom<LOGN>;
+  constexpr int N = G::N, V = G::V;
+  const int tid = threadIdx.x;
+  auto unpack = [](const float4 (&w)[V], float2 (&v)[N]) {
+#pragma unroll
+    for (int q = 0; q < V; q++) {
+      v[2 * q] = make_float2(w[q].x, w[q].y);
+      v[2 * q + 1] = make_float2(w[q].z, w[q].w);
+    }
+  };
+  auto pack = [](const float2 (&v)[N], float4 (&w)[V]) {
+#pragma unroll
+    for (int q = 0; q < V; q++) w[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+  };
+  if constexpr (!G::STAGED) {
+    const long long b0 = (long long)blockIdx.x * G::PER_CTA + tid;
+    float4 w[G::ITER][V];
+#pragma unroll
+    for (int it = 0; it < G::ITER; it++) {
+      const long long b = b0 + (long long)it * G::THREADS;
+#pragma unroll
+      for (int q = 0; q < V; q++) w[it][q] = b < batch ? __ldcs(in + b * V + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < G::ITER; it++) {
+      float2 v[N];
+      unpack(w[it], v);
+      thread_transform<LOGN, KIND, INV>(v, hw, scale);
+      pack(v, w[it]);
+    }
+    __syncthreads();  // in place: the CTA's loads are all done before its first store
+#pragma unroll
+    for (int it = 0; it < G::ITER; it++) {
+      const long long b = b0 + (long long)it * G::THREADS;
+      if (b < batch) {
+#pragma unroll
+        for (int q = 0; q < V; q++) __stcs(out + b * V + q, w[it][q]);
+      }
+    }
+  } else {
+    extern __shared__ float4 rows4[];
+    const long long base = (long long)blockIdx.x * G::PER_CTA;
+    const long long left = batch - base;
+    const int ntr = left < G::PER_CTA ? (int)left : G::PER_CTA;
+    const float4 *src = in + base * V;
+    float4 *dst = out + base * V;
+    float4 w[V];
+    if (ntr == G::PER_CTA) {  // (every CTA but the last) V independent 128-bit loads in flight per thread
+#pragma unroll
+      for (int q = 0; q < V; q++) w[q] = __ldcs(src + tid + q * G::THREADS);
+#pragma unroll
+      for (int q = 0; q < V; q++) {
+        const int i = tid + q * G::THREADS;
+        rows4[(i / V) * G::ROW4 + (i % V)] = w[q];
+      }
+    } else {
+      for (int i = tid; i < ntr * V; i += G::THREADS) rows4[(i / V) * G::ROW4 + (i % V)] = __ldcs(src + i);
+    }
+    __syncthreads();
+    if (tid < ntr) {
+      float4 *row = rows4 + tid * G::ROW4;
+#pragma unroll
+      for (int q = 0; q < V; q++) w[q] = row[q];
+      float2 v[N];
+      unpack(w, v);
+      thread_transform<LOGN, KIND, INV>(v, hw, scale);
+      pack(v, w);
+#pragma unroll
+      for (int q = 0; q < V; q++) row[q] = w[q];
+    }
+    __syncthreads();
+    if (ntr == G::PER_CTA) {
+#pragma unroll
+      for (int q = 0; q < V; q++) {
+        const int i = tid + q * G::THREADS;
+        __stcs(dst + i, rows4[(i / V) * G::ROW4 + (i % V)]);
+      }
+    } else {
+      for (int i = tid; i < ntr * V; i += G::THREADS) __stcs(dst + i, rows4[(i / V) * G::ROW4 + (i % V)]);
+    }
+  }
 }
 
 }  // namespace b2f

@@ -51,58 +51,6 @@
 
 namespace b2f {
 
-// ---- radix-32 butterfly: natural order in, natural order out ------------------------------------------------------
-template <bool INV>
-__device__ __forceinline__ void dft32(float2 (&v)[32]) {
-  constexpr float kC[16] = {1.f,
-                            0.98078528040323043f,
-                            0.92387953251128674f,
-                            0.83146961230254524f,
-                            0.70710678118654757f,
-                            0.55557023301960229f,
-                            0.38268343236508984f,
-                            0.19509032201612833f,
-                            0.f,
-                            -0.19509032201612833f,
-                            -0.38268343236508984f,
-                            -0.55557023301960229f,
-                            -0.70710678118654757f,
-                            -0.83146961230254524f,
-                            -0.92387953251128674f,
-                            -0.98078528040323043f};
-  constexpr float kS[16] = {0.f,
-                            0.19509032201612825f,
-                            0.38268343236508978f,
-                            0.55557023301960218f,
-                            0.70710678118654757f,
-                            0.83146961230254524f,
-                            0.92387953251128674f,
-                            0.98078528040323043f,
-                            1.f,
-                            0.98078528040323043f,
-                            0.92387953251128674f,
-                            0.83146961230254524f,
-                            0.70710678118654757f,
-                            0.55557023301960218f,
-                            0.38268343236508978f,
-                            0.19509032201612825f};
-  float2 e[16], o[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    e[i] = v[2 * i];
-    o[i] = v[2 * i + 1];
-  }
-  dft16<INV>(e);
-  dft16<INV>(o);
-#pragma unroll
-  for (int i = 1; i < 16; i++) o[i] = (i == 8) ? cquarter<INV>(o[i]) : cmulc<INV>(o[i], kC[i], kS[i]);
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    v[i] = cadd(e[i], o[i]);
-    v[i + 16] = csub(e[i], o[i]);
-  }
-}
-
 // v[m] *= W^m for m = 1..31, given W^1, W^2, W^4, W^8, W^16 (base[b] = W^(2^b)): the other 26 powers are products
 // built depth-first over the bits of m, so at most four partial products are alive at a time (26 complex
 // multiplications, at most four roundings deep, ~3e-7) -- the full table of a pass would be 31 loads per

@@ -74,6 +74,40 @@ def test_cfft_batched(eng, port, logn, batch):
     assert p.transform(np.zeros((batch + 1) * N, np.complex64)) == 6  # over max_batch
 
 
+@pytest.mark.parametrize("logn", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("batch", [1, 127, 128, 129, 1023, 1025, 2500])
+def test_one_thread_per_transform_kernels_every_transform(eng, port, logn, batch):
+    """N <= 32 run one thread per transform (fft_thread_kernel): batches that end inside a CTA, on a CTA
+    boundary and one past it; complex both ways, real forward and inverse, every transform checked."""
+    N = 1 << logn
+    rng = np.random.default_rng(77 * logn + batch)
+    x = crand(rng, batch, N)
+    for fwd in (True, False):
+        y = x.copy()
+        assert eng.Clcfft(0, N, fwd, max_batch=batch).transform(y.reshape(-1)) == 0
+        x64 = x.astype(np.complex128)
+        truth = np.fft.fft(x64, axis=1) / N if fwd else np.fft.ifft(x64, axis=1) * N
+        assert max(rel_l2(y[b], truth[b]) for b in range(batch)) < 2e-6
+        for b in (0, batch // 2, batch - 1):
+            assert rel_l2(y[b], port.cfft(x[b], fwd)) < TOL
+    size = 2 * N
+    r = rng.uniform(-1, 1, (batch, size)).astype(np.float32)
+    c = np.zeros((batch, N), np.complex64)
+    assert eng.Clrfft(0, size, True, max_batch=batch).transform(c.reshape(-1), r.reshape(-1).copy()) == 0
+    X = np.fft.rfft(r.astype(np.float64), axis=1)
+    want = 2 * X[:, :N] / size
+    want[:, 0] = (X[:, 0].real + 1j * X[:, N].real) / size  # packed (DC, Nyquist), Q2
+    want[:, N // 2] = np.conj(want[:, N // 2])  # Q3: bin size/4 conjugated
+    assert max(rel_l2(c[b], want[b]) for b in range(batch)) < 2e-6
+    for b in (0, batch // 2, batch - 1):
+        assert rel_l2(c[b], port.rfft_fwd(r[b])) < TOL
+    back = np.zeros((batch, size), np.float32)
+    assert eng.Clrfft(0, size, False, max_batch=batch).transform(c.reshape(-1), back.reshape(-1)) == 0
+    assert np.abs(back - r).max() < 2e-5
+    for b in (0, batch - 1):
+        assert rel_l2(back[b], port.rfft_inv(port.rfft_fwd(r[b]))) < TOL
+
+
 def test_golden_cfft_rfft(eng, golden):
     g = golden
     for fwd, key in ((True, "cfft1024_fwd"), (False, "cfft1024_inv")):
