@@ -60,7 +60,8 @@ const char *b2f_version(void);
  * runtime configuration: the constructor arguments stay the only per-object input and
  * every default below is the measured winner.
  *   fft_sm_min_batch  96     N = 32768 complex / 65536 real: the one-SM kernel from this batch up
- *                            (0 never, 1 always); below it the four-step launch pair
+ *                            (0 never, 1 always); below it the four-step launch pair. N = 16384 / 32768 real:
+ *                            from twice this batch up (two transforms per CTA iteration); below, one CTA each
  *   large_chunk_mb    256    scratch chunk of the four-step launch pair
  *   rows_rb16         0      16-row CTAs in the four-step real rows kernel
  *   separate_split    0      unfused real split / unsplit pass on the four-step path
@@ -71,6 +72,8 @@ const char *b2f_version(void);
  *                            channels), FFT batches above 1 MB (eight chunks of the batch)
  *   zerocopy_max      65536  host calls moving at most this many bytes run on pinned buffers directly
  *   graph             1      CUDA graph replay for the multi-launch host paths (pts >= 8192)
+ *   fft_prefetch      -1     real transforms of 8192 / 16384 complex points, one CTA each: L2 prefetch of the
+ *                            transform this many CTAs ahead (-1: the co-resident CTAs, 0: off)
  *   verbose           0
  * Unknown names return B2F_ERR_INVALID_VALUE. */
 int b2f_set_option(const char *name, long long value);

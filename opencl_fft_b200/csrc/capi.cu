@@ -74,6 +74,7 @@ struct Options {
   long long pconv_pipeline = 1;      // two-stream host calls (pconv: halves of the channels; FFT: chunks of the batch)
   long long zerocopy_max = 65536;    // host calls up to this many bytes run on the pinned buffers directly
   long long graph = 1;               // CUDA graph for the multi-launch host paths
+  long long fft_prefetch = -1;       // real one-CTA transforms of N >= 8192: L2 prefetch distance in CTAs (-1: the resident CTAs, 0: off)
   long long verbose = 0;
 };
 struct OptionName {
@@ -90,6 +91,7 @@ static const OptionName kOptionNames[] = {
     {"pconv_pipeline", "B2F_PCONV_PIPELINE", &Options::pconv_pipeline},
     {"zerocopy_max", "B2F_ZEROCOPY_MAX", &Options::zerocopy_max},
     {"graph", "B2F_GRAPH", &Options::graph},
+    {"fft_prefetch", "B2F_FFT_PREFETCH", &Options::fft_prefetch},
     {"verbose", "B2F_VERBOSE", &Options::verbose},
 };
 static std::mutex g_opt_mutex;
@@ -248,6 +250,26 @@ static int set_smem(K kernel, int bytes) {
   return bytes > 48 * 1024 ? set_smem_once((const void *)kernel, bytes) : B2F_OK;
 }
 
+// SM count of the device the running entry point made current
+static int sm_count() {
+  static std::mutex m;
+  static int cached[64] = {0};
+  const int d = g_device < 0 ? 0 : (g_device & 63);
+  std::lock_guard<std::mutex> lk(m);
+  if (!cached[d]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n < 1) n = 148;
+    cached[d] = n;
+  }
+  return cached[d];
+}
+// L2 prefetch distance of the real one-transform-per-CTA kernels, in CTAs: option fft_prefetch, -1 = the CTAs resident at a time
+template <class B>
+static int prefetch_distance(long long opt) {
+  if (!B::PREFETCH || opt == 0) return 0;
+  return opt > 0 ? (int)opt : sm_count() * B::MIN_BLOCKS;
+}
+
 template <int LOGN>
 static int launch_cfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, int batch, float scale,
                          cudaStream_t st) {
@@ -281,7 +303,7 @@ static int launch_cfft_t(bool inv, const float2 *in, float2 *out, const float2 *
 }
 template <int LOGN>
 static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *hw, int batch,
-                         float fwd_scale, cudaStream_t st) {
+                         float fwd_scale, cudaStream_t st, long long prefetch) {
   if constexpr (ThreadGeom<LOGN>::OK) {  // one thread per transform, split / unsplit in registers (N = 2, 4, 32)
     using G = ThreadGeom<LOGN>;
     const int grid = (batch + G::PER_CTA - 1) / G::PER_CTA;
@@ -298,14 +320,15 @@ static int launch_rfft_t(bool inv, const float2 *in, float2 *out, const float2 *
     using B = BatchGeom<LOGN>;
     const int grid = (batch + B::TPB - 1) / B::TPB;
     // register-level split / unsplit (fft_kernels.cuh, second half)
+    const int ahead = prefetch_distance<B>(prefetch);
     if (inv) {
       int rc = set_smem(rfft_inv_reg_kernel<LOGN>, B::SMEM_BYTES);
       if (rc) return rc;
-      rfft_inv_reg_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, hw, batch);
+      rfft_inv_reg_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, hw, batch, ahead);
     } else {
       int rc = set_smem(rfft_fwd_reg_kernel<LOGN>, B::SMEM_BYTES);
       if (rc) return rc;
-      rfft_fwd_reg_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, hw, batch, fwd_scale);
+      rfft_fwd_reg_kernel<LOGN><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(in, out, tw, hw, batch, fwd_scale, ahead);
     }
   } else {
     static_assert(LOGN < 0, "every size has a real-transform kernel");
@@ -340,8 +363,8 @@ static int launch_cfft(int logn, bool inv, const float2 *in, float2 *out, const 
 #undef CALL
 }
 static int launch_rfft(int logn, bool inv, const float2 *in, float2 *out, const float2 *tw, const float2 *hw, int batch,
-                       float fwd_scale, cudaStream_t st) {
-#define CALL(L) launch_rfft_t<L>(inv, in, out, tw, hw, batch, fwd_scale, st)
+                       float fwd_scale, cudaStream_t st, long long prefetch) {
+#define CALL(L) launch_rfft_t<L>(inv, in, out, tw, hw, batch, fwd_scale, st, prefetch)
   B2F_DISPATCH_LOGN(logn, CALL)
 #undef CALL
 }
@@ -392,8 +415,7 @@ struct SmPlan {
   }
   template <bool INV, int KIND>
   int run(const float2 *in, float2 *out, const float2 *hw, int batch, float scale, cudaStream_t st) {
-    if constexpr (KIND == kSmComplex)
-      if (logn == 14) return run_t<INV, KIND, 4>(in, out, hw, batch, scale, st);
+    if (logn == 14) return run_t<INV, KIND, 4>(in, out, hw, batch, scale, st);
     return run_t<INV, KIND, 5>(in, out, hw, batch, scale, st);
   }
 };
@@ -599,7 +621,7 @@ struct FftPlanCore {
       rc = upload(make_pass_twiddles(logn), &d_tw);
       if (rc) return rc;
     }
-    if ((logn == SmGeom::LOGN || (logn == 14 && !real)) && opt.fft_sm_min_batch > 0) {
+    if ((logn == SmGeom::LOGN || logn == 14) && opt.fft_sm_min_batch > 0) {
       sm.min_batch = opt.fft_sm_min_batch;
       rc = sm.init(dev, logn);
       if (rc) return rc;
@@ -681,7 +703,7 @@ struct FftPlanCore {
       return fwd ? sm.run<false, kSmRealFwd>(in, out, d_hw, batch, fwd_scale(), st)
                  : sm.run<true, kSmRealInv>(in, out, d_hw, batch, 1.0f, st);
     if (is_large()) return large.run_real(!fwd, in, out, d_w2, d_hw, batch, fwd_scale(), st);
-    return launch_rfft(logn, !fwd, in, out, d_tw, d_hw, batch, fwd_scale(), st);
+    return launch_rfft(logn, !fwd, in, out, d_tw, d_hw, batch, fwd_scale(), st, opt.fft_prefetch);
   }
 };
 

@@ -11,6 +11,7 @@
 #pragma once
 
 #include "fft_core.cuh"
+#include "tma_utils.cuh"
 
 namespace b2f {
 
@@ -27,7 +28,27 @@ struct BatchGeom {
   static constexpr int ROW = G::SMEM;
   static constexpr int SMEM_BYTES = TPB * ROW * (int)sizeof(float2);
   static constexpr int MIN_BLOCKS = 1024 / THREADS;  // caps registers at 64/thread: 32 resident warps per SM
+  // real transforms of N >= 8192: the CTA asks the TMA engine for the transform of the CTA `ahead` further on (the one
+  // that takes its place when it retires; the host passes the number of co-resident CTAs) while it works
+  static constexpr bool PREFETCH = LOGN >= 13;
 };
+// A CTA's loads are all issued in its first few hundred cycles and then waited for; with 1-2 CTAs of 512-1024 threads
+// per SM there is little else in flight meanwhile. Prefetched into L2 while the predecessor computes, they come back
+// at L2 latency instead. Measured (fraction of the HBM peak, r2c / c2r): N = 8192 0.64 / 0.58 -> 0.67 / 0.61,
+// N = 16384 0.49 / 0.46 -> 0.53 / 0.50; no gain at N <= 4096, and the complex kernels LOSE with it (N = 1024..4096:
+// 1.04 -> 0.93..0.97; N = 8192: 0.72 -> 0.71 -- ncu of cfft_kernel<13>: the LSU data pipe, 59 % busy over the whole
+// kernel and saturated in the load and store phases, is what limits them, not the latency of the loads), so only
+// the real kernels use it.
+template <int LOGN>
+__device__ __forceinline__ void prefetch_successor(const float2 *in, int ahead, int batch) {
+  using B = BatchGeom<LOGN>;
+  if constexpr (B::PREFETCH) {
+    constexpr int N = 1 << LOGN, CHUNKS = B::TPB * N * (int)sizeof(float2) / 4096;
+    const long long first = ((long long)blockIdx.x + ahead) * B::TPB;  // first transform of the successor CTA
+    if (ahead > 0 && (int)threadIdx.x < CHUNKS && first * N + ((int)threadIdx.x + 1) * 512 <= (long long)batch * N)
+      tma::prefetch_l2(in + first * N + threadIdx.x * 512, 4096);
+  }
+}
 
 // ---- complex to complex ------------------------------------------------------------------------
 // in/out: [batch][N] float2, may alias (each CTA gathers its whole transform before it scatters).
@@ -92,7 +113,7 @@ struct RegSplitGeom {
 template <int LOGN>
 __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
     rfft_fwd_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
-                        int batch, float scale) {
+                        int batch, float scale, int ahead) {
   using B = BatchGeom<LOGN>;
   constexpr int N = 1 << LOGN, T = B::T, E = FftGeom<LOGN>::E, H = E / 2;
   extern __shared__ float2 smem[];
@@ -103,6 +124,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   float2 *dst = out + (active ? b : 0) * N;
   float2 *sm = smem + lt * BatchGeom<LOGN>::ROW;
   float2 x[E];
+  prefetch_successor<LOGN>(in, ahead, batch);
   auto load = [&](int idx, int) { return active ? __ldcs(src + idx) : make_float2(0.f, 0.f); };
   auto store = [&](int, float2 v, int slot) { x[slot] = v; };  // last pass: slot == m, value X[t + m*T]
   fft_run<LOGN, false>(load, store, sm, tw, t, CtaSync());
@@ -136,7 +158,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
 template <int LOGN>
 __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
     rfft_inv_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
-                        int batch) {
+                        int batch, int ahead) {
   using B = BatchGeom<LOGN>;
   using RS = RegSplitGeom<LOGN>;
   constexpr int N = 1 << LOGN, T = B::T, R0 = RS::R0, E = FftGeom<LOGN>::E, H = E / 2;
@@ -150,6 +172,7 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   // a thread reads its 8 low members X[t + m*T] and, straight from global memory, their partners X[N - (t + m*T)]
   // (the values its partner thread will own): 16 loads as before, and no exchange before the unsplit
   float2 x[E], hi[H];  // hi: unsplit high members, owned by the partner thread
+  prefetch_successor<LOGN>(in, ahead, batch);
   const int pt = (t == 0) ? 0 : T - t;
   const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll

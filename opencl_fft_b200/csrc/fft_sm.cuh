@@ -190,9 +190,10 @@ __device__ constexpr float kSplitS[32] = {
 // keeps its own member of each pair. In the rows, the column groups j2 are stored permuted (0..7, 24..31, 8..23) so
 // that round 0 still writes the first halves and round 1 the second.
 //
-// LOG1 = 4 (N = 16 x 32 x 32 = 2^14, complex only): the same kernel carries TWO transforms per unit of work -- the 32
-// staged runs are the 16 runs of each, P1 is two radix-16 butterflies per column, job 0 is the first transform's 16
-// rows and job 1 the second's (parked in tensor memory meanwhile); passes A and B are unchanged.
+// LOG1 = 4 (N = 16 x 32 x 32 = 2^14): the same kernel carries TWO transforms per unit of work -- the 32 staged runs
+// are the 16 runs of each, P1 is two radix-16 butterflies per column, job 0 is the first transform's 16 rows and job 1
+// the second's (parked in tensor memory meanwhile); passes A and B are unchanged. Real transforms: the unsplit pairs
+// runs j1 <-> 15 - j1 of the same transform; the split stays inside a job (see pass B).
 enum { kSmComplex = 0, kSmRealFwd = 1, kSmRealInv = 2 };
 template <bool INV, int KIND, int LOG1 = 5>
 __global__ void __launch_bounds__(SmGeom::THREADS, 1)
@@ -201,11 +202,11 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   using G = SmGeom;
   constexpr bool REAL = (KIND == kSmRealFwd), C2R = (KIND == kSmRealInv);
   static_assert(!(REAL && INV) && !(C2R && !INV), "the split follows a forward, the unsplit precedes an inverse transform");
-  static_assert(LOG1 == 5 || (LOG1 == 4 && KIND == kSmComplex), "two transforms per unit: complex only");
+  static_assert(LOG1 == 5 || LOG1 == 4, "N = 2^15, or two transforms of 2^14 per unit");
   constexpr int N1 = 1 << LOG1, NTR = 32 / N1;  // radix of P1, transforms per unit
   constexpr int N = N1 * 1024;
   const int units = (batch + NTR - 1) / NTR;
-  constexpr int TCOLS = REAL ? G::TCOLS_THREAD_R : G::TCOLS_THREAD_C;
+  constexpr int TCOLS = (REAL && LOG1 == 5) ? G::TCOLS_THREAD_R : G::TCOLS_THREAD_C;
   extern __shared__ __align__(16) unsigned char smraw[];
   unsigned char *rows = smraw;
   float2 *Z = reinterpret_cast<float2 *>(smraw + G::OFF_Z);
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   }
   if constexpr (REAL || C2R)
     for (int i = tid; i < 1024; i += G::THREADS) hwb[i] = __ldg(&hw[i]);
-  if constexpr (REAL) hw32[tid] = __ldg(&hw[32 * ((tid >> 4) + 32 * (tid & 15))]);  // [k2][k3 < 16]: entry 32 m, m = k2 + 32 k3
+  if constexpr (REAL) hw32[tid] = __ldg(&hw[N1 * ((tid >> 4) + 32 * (tid & 15))]);  // [k2][k3 < 16]: entry N1 m, m = k2 + 32 k3
   if (warp == 0) tmem::alloc((uint32_t)__cvta_generic_to_shared(misc), 4 * TCOLS);
   tmem::fence_before();
   __syncthreads();
@@ -298,22 +299,22 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
         // byte offset of a column inside a staged run
         auto off = [&](int col) { return r == 0 ? (col < 258 ? col * 8 : (col - 510) * 8) : (col - 256) * 8; };
         const bool col0 = (c == 0);
-        const int oc = off(c), opc = off(col0 ? 0 : 1024 - c), pj0 = col0 ? 32 : 31;
+        const int oc = off(c), opc = off(col0 ? 0 : 1024 - c), pj0 = col0 ? N1 : N1 - 1;
         const float2 hbase = hwb[c];
-        float2 raw0 = make_float2(0.f, 0.f), raw16 = raw0;
+        float2 raw[32];  // (only raw[0], raw[N1/2] of every transform are used, and only in column 0)
 #pragma unroll
         for (int j = 0; j < 32; j++) {
+          const int j1 = j % N1, jt = j - j1;  // run j1 of transform jt / N1 of the unit
           const float2 a = *reinterpret_cast<const float2 *>(run_base(r, j) + oc);
-          // partner run 31 - j (32 - j in column 0: a different run per lane there, so the address is computed)
-          const int pj = (pj0 - j) & 31;
+          // partner run N1 - 1 - j1 (N1 - j1 in column 0: a different run per lane there, so the address is computed)
+          const int pj = jt + ((pj0 - j1) & (N1 - 1));
           const unsigned char *pb = r == 0 ? rows + pj * RUN : (pj < 16 ? rows + pj * G::ROW + 4096 : sp + (pj - 16) * RUN);
           const float2 b = *reinterpret_cast<const float2 *>(pb + opc);
-          if (j == 0) raw0 = a;
-          if (j == 16) raw16 = a;
-          // hw(1024 j + c) = hw(c) exp(+i pi j / 32), extended analytically past N/2, where hw(N - i) = conj(hw(i))
-          const float2 hk = j ? cmulc<true>(hbase, kSplitC[j], kSplitS[j]) : hbase;
+          raw[j] = a;
+          // hw(1024 j1 + c) = hw(c) exp(+i pi j1 / N1), extended analytically past N/2, where hw(N - i) = conj(hw(i))
+          const float2 hk = j1 ? cmulc<true>(hbase, kSplitC[j1 * (32 / N1)], kSplitS[j1 * (32 / N1)]) : hbase;
           float2 A = a, B = b;
-          if (j < 16) {
+          if (j1 < N1 / 2) {
             rfft_pair_folded<true>(A, B, hk, 0.5f);
             v[j] = A;
           } else {
@@ -322,8 +323,11 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
           }
         }
         if (col0) {  // element 0: packed (DC, Nyquist); element N/2: never visited by the reference (cl_fft.cpp:286)
-          v[0] = rfft_dc<true>(raw0);
-          v[16] = raw16;
+#pragma unroll
+          for (int jt = 0; jt < 32; jt += N1) {
+            v[jt] = rfft_dc<true>(raw[jt]);
+            v[jt + N1 / 2] = raw[jt + N1 / 2];
+          }
         }
       }
       __syncthreads();  // the round is in registers: its half of the row buffers may be written
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
         int tr = (t + gridDim.x) * NTR + tid / N1;
         tr = tr < batch ? tr : batch - 1;
         const float2 *nx = in + (size_t)tr * N + 1024 * (tid % N1) + 512 * job;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx), "r"(4096) : "memory");
+        tma::prefetch_l2(nx, 4096);
       }
       if (job == 1) {
         // the second job's rows: tensor memory -> row buffers
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
         const int s = lane & 15, h = lane >> 4;
         // Real transform, job 0: the lane takes the row and the k2 its job-1 self will need as partner, i.e. row
         // (16 - s) mod 16 and the warp's OTHER k2 -- what it parks in tensor memory is then its own partner data.
-        const bool mirrored = REAL && job == 0;
+        const bool mirrored = REAL && LOG1 == 5 && job == 0;
         const int slot = mirrored ? ((16 - s) & 15) : s;
         const int k2 = (h != (int)mirrored) ? 31 - warp : warp;
         const int k1 = LOG1 == 5 ? 16 * job + slot : slot;  // LOG1 = 4: job = transform of the unit, rows 0..15 each
@@ -443,6 +447,72 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
           if (LOG1 == 5 || t * NTR + job < batch) {  // (the second transform of the last unit of an odd batch)
 #pragma unroll
             for (int k3 = 0; k3 < 32; k3++) B2F_SMX_STG(o[32 * N1 * k3], cscale(v[k3], scale));
+          }
+        } else if constexpr (LOG1 == 4) {
+          // Two transforms per unit: the partner (16 - k1, 31 - k2, 31 - k3) is in the SAME job -- the warp's other k2,
+          // row slot 16 - s. Every lane hands the upper half of its results (k3 >= 16) over through the round-1 staging
+          // area (idle during pass B; 16-byte chunk q of slot s sits at position q ^ (s & 7): conflict-free both ways),
+          // evaluates the 16 pairs of its lower half and stores both members. Row 0 ((k2, k3) <-> (32 - k2, 31 - k3),
+          // across warps) is split in Z between two barriers and stored by the s = 0 lanes in the same instructions.
+          float4 *xch = reinterpret_cast<float4 *>(sp);  // [k2][slot][8 chunks]
+          if (s == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; q++)
+              *reinterpret_cast<float4 *>(Z + 32 * k2 + 2 * q) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+              xch[(k2 * 16 + s) * 8 + (q ^ (s & 7))] = make_float4(v[16 + 2 * q].x, v[16 + 2 * q].y, v[17 + 2 * q].x, v[17 + 2 * q].y);
+          }
+          __syncthreads();
+          {  // row k1 = 0: X[N1 m], m = k2 + 32 k3, pairs (m, 1024 - m); m = 0 packed (DC, Nyquist), m = 512 is bin N/2
+            const int zk3 = tid & 15, zk2 = tid >> 4, m = zk2 + 32 * zk3;
+            if (m == 0) {
+              const float2 z0 = Z[0];
+              Z[0] = make_float2((z0.x + z0.y) * hs, (z0.x - z0.y) * hs);
+              Z[16] = cscale(Z[16], scale);
+            } else {
+              const int pi = zk2 ? 32 * (32 - zk2) + 31 - zk3 : 32 - zk3;
+              float2 a = Z[32 * zk2 + zk3], b = Z[pi];
+              rfft_pair_folded<false>(a, b, hw32[tid], hs);
+              Z[32 * zk2 + zk3] = a;
+              Z[pi] = b;
+            }
+          }
+          __syncthreads();
+          float2 pk[16];  // pk[i]: result 16 + i of the partner (row 0: of row 0, column group 31 - k2)
+          if (s == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const float4 f = *reinterpret_cast<const float4 *>(Z + 32 * k2 + 2 * q);
+              const float4 g = *reinterpret_cast<const float4 *>(Z + 32 * (31 - k2) + 16 + 2 * q);
+              v[2 * q] = make_float2(f.x, f.y);
+              v[2 * q + 1] = make_float2(f.z, f.w);
+              pk[2 * q] = make_float2(g.x, g.y);
+              pk[2 * q + 1] = make_float2(g.z, g.w);
+            }
+          } else {
+            const int ps = 16 - s;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const float4 g = xch[((31 - k2) * 16 + ps) * 8 + (q ^ (ps & 7))];
+              pk[2 * q] = make_float2(g.x, g.y);
+              pk[2 * q + 1] = make_float2(g.z, g.w);
+            }
+            const float2 hbase = hwb[k1 + N1 * k2];
+#pragma unroll
+            for (int k3 = 0; k3 < 16; k3++) {
+              const float2 hk = k3 ? cmulc<false>(hbase, kSplitC[k3], kSplitS[k3]) : hbase;
+              rfft_pair_folded<false>(v[k3], pk[15 - k3], hk, hs);
+            }
+          }
+          if (t * NTR + job < batch) {
+            float2 *om = dst + (size_t)job * N + ((16 - s) & 15) + N1 * (31 - k2) + 32 * N1 * 31;
+#pragma unroll
+            for (int k3 = 0; k3 < 16; k3++) {
+              B2F_SMX_STG(o[32 * N1 * k3], v[k3]);
+              B2F_SMX_STG(om[-32 * N1 * k3], pk[15 - k3]);
+            }
           }
         } else if (job == 0) {
           if (s == 0) {  // row 0 -> Z[k2][k3]
@@ -515,9 +585,10 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
           }
         }
       }
-      if (job == 0) __syncthreads();  // the row buffers are free again and Z is complete (job 1: m_free, and P1's barrier)
+      // the row buffers are free again and Z is complete (job 1: m_free, and P1's barrier; real LOG1 = 4: pass B's own)
+      if (job == 0 && !(REAL && LOG1 == 4)) __syncthreads();
 
-      if constexpr (REAL) {
+      if constexpr (REAL && LOG1 == 5) {
         if (job == 0) {
           // row k1 = 0: X[32 m], m = k2 + 32 k3, pairs (m, 1024 - m), split in place; m = 0 is the packed (DC, Nyquist)
           // element and m = 512 is bin N/2, which the reference's split never visits (cl_fft.cpp:278).

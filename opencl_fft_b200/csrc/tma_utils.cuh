@@ -48,6 +48,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                "l"(src), "r"(bytes), "r"(mbar)
                : "memory");
 }
+// ask the TMA engine to bring `bytes` (multiple of 16) of global memory into L2: no registers, no shared memory, no
+// completion to wait for (SASS UBLKPF)
+__device__ __forceinline__ void prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 }  // namespace tma
 
 }  // namespace b2f

@@ -293,6 +293,42 @@ def test_one_sm_kernel_16384_point_complex(eng, options, batch):
     assert rel_l2(got[1, True], got[0, True]) < 1e-6 and rel_l2(got[1, False], got[0, False]) < 1e-6
 
 
+@pytest.mark.parametrize("batch", [1, 2, 3, 149, 297, 300])
+def test_one_sm_kernel_32768_point_real(eng, port, options, batch):
+    """The 32768-point real transform (N = 2^14 complex) on the one-SM kernel: the split pairs lanes of one warp inside a
+    job and row 0 across warps, the unsplit pairs staged runs j1 <-> 15 - j1 of the same transform. Every transform,
+    forward and inverse, against float64 with the reference's quirks (Q2, Q3), a few against the oracle; run twice
+    (bit-identical); the default selection for small batches (one CTA per transform) must agree to rounding."""
+    size = 32768
+    rng = np.random.default_rng(1000 + batch)
+    x = rng.uniform(-1, 1, (batch, size)).astype(np.float32)
+    X = np.fft.rfft(x.astype(np.float64), axis=1)
+    want = 2 * X[:, : size // 2] / size
+    want[:, 0] = (X[:, 0].real + 1j * X[:, size // 2].real) / size
+    want[:, size // 4] = np.conj(want[:, size // 4])
+    got = {}
+    for forced in (1, 0):
+        options("fft_sm_min_batch", forced)
+        f, inv = eng.Clrfft(0, size, True, max_batch=batch), eng.Clrfft(0, size, False, max_batch=batch)
+        outs = []
+        for _ in range(2):
+            c = np.zeros((batch, size // 2), np.complex64)
+            assert f.transform(c.reshape(-1), x.reshape(-1).copy()) == 0
+            outs.append(c)
+        assert np.array_equal(outs[0], outs[1])
+        err = np.linalg.norm(outs[0] - want, axis=1) / np.linalg.norm(want, axis=1)
+        assert err.max() < 2e-6, (forced, int(err.argmax()), float(err.max()))
+        for b in (0, batch - 1):
+            assert rel_l2(outs[0][b], port.rfft_fwd(x[b])) < TOL
+        back = np.zeros((batch, size), np.float32)
+        assert inv.transform(outs[0].copy().reshape(-1), back.reshape(-1)) == 0
+        err = np.linalg.norm(back - x, axis=1) / np.linalg.norm(x, axis=1)
+        assert err.max() < 2e-6, (forced, int(err.argmax()), float(err.max()))
+        assert rel_l2(back[batch - 1], port.rfft_inv(port.rfft_fwd(x[batch - 1]))) < TOL
+        got[forced] = (outs[0], back)
+    assert rel_l2(got[1][0], got[0][0]) < 1e-6 and rel_l2(got[1][1], got[0][1]) < 1e-6
+
+
 @pytest.mark.parametrize("size,batch", [(4096, 1031), (65536, 800)])
 def test_pipelined_host_call_equals_single_stream(eng, options, size, batch):
     """Host calls above 1 MB cut the batch into chunks alternating between two streams (upload, transform and download
