@@ -874,18 +874,18 @@ struct b2f_pconv {
 };
 
 template <int LOGP>
-static int pconv_smem_bytes(bool tv, bool tma) {
+static int pconv_smem_bytes(bool tv, bool tma, int S) {
   using P = PconvGeom<LOGP>;
   const int fft = P::FFT_SMEM + (P::FFT_SMEM & 1);
-  const int partial4 = (P::TILES > 1 ? 2 : 1) * P::HALF;
-  const int ring = tma ? P::RING_F4 * (int)sizeof(float4) + 2 * P::STAGES * 8 : 0;
+  const int partial4 = P::partial_f4(tma, S);
+  const int ring = tma ? P::ring_f4(tv) * (int)sizeof(float4) + 2 * P::stages(tv) * 8 : 0;
   return (tv ? 2 : 1) * fft * (int)sizeof(float2) + partial4 * (int)sizeof(float4) + ring;
 }
 
 template <int LOGP, bool TV, bool TMA>
 static int launch_pconv_step_tt(const PconvArgs &a, int channels, int S, cudaStream_t st) {
   using P = PconvGeom<LOGP>;
-  const int smem = pconv_smem_bytes<LOGP>(TV, TMA);
+  const int smem = pconv_smem_bytes<LOGP>(TV, TMA, S);
   int rc = set_smem(pconv_step_kernel<LOGP, TV, TMA>, smem);
   if (rc) return rc;
   cudaLaunchConfig_t cfg = {};

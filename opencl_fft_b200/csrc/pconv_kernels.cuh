@@ -43,9 +43,23 @@ struct PconvGeom {
   static constexpr int FFT_SMEM = VT * G::SMEM;            // float2 entries per FFT work buffer
   // TMA-fed MAC: one extra (producer) warp, a ring of STAGES x {FDL slice, IR slice} of SLICE float4 each
   // (4096-sample partitions leave room for one CTA per SM only: a deeper ring keeps enough bytes in flight)
-  static constexpr int STAGES = LOGP >= 12 ? 10 : 6;  // (10: the time-varying variant, with two FFT buffers, still fits 227 KB)
+  // pts 4096: 5 stages of 8 KB, so that TWO CTAs fit an SM (107 KB each) and one streams while the other runs its
+  // transforms. Measured on one box, 1024 / 256 channels x 117 partitions, fraction of the HBM peak: one CTA per SM
+  // with 10 stages 0.81 / 0.71, 20 stages 0.80 / 0.70, 20 stages + ring filled before the forward transform
+  // 0.77 / 0.67 -- depth was never the limit, the serial phases of a lone CTA were.
+#ifndef B2F_PCONV_STAGES12
+#define B2F_PCONV_STAGES12 5  // (build-time knob kept for re-measurement)
+#endif
+  __host__ __device__ static constexpr int stages(bool) { return LOGP >= 12 ? B2F_PCONV_STAGES12 : 6; }
   static constexpr int SLICE = HALF < NTHREADS ? HALF : NTHREADS;  // float4 per slice (16 B .. 4 KB)
-  static constexpr int RING_F4 = 2 * STAGES * SLICE;
+  __host__ __device__ static constexpr int ring_f4(bool tv) { return 2 * stages(tv) * SLICE; }
+  // frames wider than the CTA whose tiles are swept together, one accumulator per tile (see pconv_step_kernel)
+  __host__ __device__ static constexpr bool pmajor(bool tma) { return TILES > 1 && (tma || TILES == 2 || TILES == 4); }
+  // float4 entries between the FFT buffers and the TMA ring: the cluster-partials buffer (clusters only), then the
+  // buffer the tile-by-tile sweep parks Y in
+  __host__ __device__ static constexpr int partial_f4(bool tma, int S) {
+    return (S > 1 ? HALF : 0) + (TILES > 1 && !pmajor(tma) ? HALF : 0);
+  }
 };
 
 // barrier over the FFT participants only (warps 0 .. FT/32-1); id 1, the CTA barrier is id 0
@@ -194,16 +208,22 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
   extern __shared__ float4 smem4[];
   float2 *sX = reinterpret_cast<float2 *>(smem4);         // new input spectrum, later Y / IFFT buffer
   float2 *sG = sX + P::FFT_SMEM + (P::FFT_SMEM & 1);      // new IR spectrum (TV only)
-  float4 *sP = reinterpret_cast<float4 *>(sG + (TV ? P::FFT_SMEM + (P::FFT_SMEM & 1) : 0));  // partials [HALF]
-  float4 *ring = sP + (P::TILES > 1 ? 2 : 1) * HALF;      // TMA ring: [STAGES][2][SLICE] float4, then barriers
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  float4 *sP = reinterpret_cast<float4 *>(sG + (TV ? P::FFT_SMEM + (P::FFT_SMEM & 1) : 0));  // cluster partials [HALF], S > 1
+  float4 *sPark = sP + (S > 1 ? HALF : 0);                // Y of the tile-by-tile sweep [HALF]
+  constexpr int STAGES = P::stages(TV), RING_F4 = P::ring_f4(TV);
+  constexpr bool PMAJOR = P::pmajor(TMA);
+  float4 *ring = sP + P::partial_f4(TMA, S);              // TMA ring: [STAGES][2][SLICE] float4, then barriers
   const bool worker = !TMA || threadIdx.x < NT;           // false only for the producer warp
   uint32_t bar_full = 0, bar_empty = 0, slot = 0;         // slot: running ring position, identical in all threads
   if (TMA) {
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + P::RING_F4);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + RING_F4);
     bar_full = tma::smem_u32(bars);
-    bar_empty = tma::smem_u32(bars + P::STAGES);
+    bar_empty = tma::smem_u32(bars + STAGES);
     if (threadIdx.x == 0) {
-      for (int s = 0; s < P::STAGES; s++) {
+      for (int s = 0; s < STAGES; s++) {
         tma::mbar_init(bar_full + 8 * s, 1);         // the producer's expect_tx arrive + the bytes
         tma::mbar_init(bar_empty + 8 * s, NT / 32);  // one arrive per consumer warp
       }
@@ -212,9 +232,6 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
     __syncthreads();
   }
 
-  cg::cluster_group cluster = cg::this_cluster();
-  const int S = (int)cluster.num_blocks();
-  const int rank = (int)cluster.block_rank();
   const int ch = blockIdx.y;
   const int tid = threadIdx.x;
   const int nparts = a.nparts;
@@ -222,20 +239,6 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
   float2 *fdl = a.fdl + chan_off;
   float2 *irs = a.irs + chan_off;
 
-  // ---- 1. forward transforms of the new block(s): rank 0 only -------------------------------------
-  if (rank == 0) {
-    pconv_forward_frame<LOGP>(a.in1 + (size_t)ch * PTS, sX, a.tw, a.w2);
-    if (TV) pconv_forward_frame<LOGP>(a.in2 + (size_t)ch * PTS, sG, a.tw, a.w2);
-    // store the new frames for future blocks (this launch never reads them back from HBM)
-    float2 *fx = fdl + (size_t)a.wp * PTS;
-    for (int i = tid; i < PTS && worker; i += NT) fx[i] = sX[pad_idx(i)];
-    if (TV) {
-      float2 *gx = irs + (size_t)a.wp2 * PTS;
-      for (int i = tid; i < PTS && worker; i += NT) gx[i] = sG[pad_idx(i)];
-    }
-  }
-
-  // ---- 2. spectral multiply-accumulate over this rank's partitions --------------------------------
   // After the reference's increment (cl_conv.cpp:424) the read base is rp = wp+1 (mod nparts): the
   // oldest frame. Partition p pairs FDL frame (rp+p) mod nparts with IR frame p; p = nparts-1 is the
   // frame just written. In TV mode IR frame wp2 is also new.
@@ -255,7 +258,22 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
   const int p_newg = TV ? a.wp2 : -1;
   const size_t stride4 = HALF;
 
-  if constexpr (P::TILES > 1 && (TMA || P::TILES == 2 || P::TILES == 4)) {
+  // ---- 1. forward transforms of the new block(s): rank 0 only -------------------------------------
+  if (rank == 0) {
+    pconv_forward_frame<LOGP>(a.in1 + (size_t)ch * PTS, sX, a.tw, a.w2);
+    if (TV) pconv_forward_frame<LOGP>(a.in2 + (size_t)ch * PTS, sG, a.tw, a.w2);
+    // store the new frames for future blocks (this launch never reads them back from HBM)
+    float2 *fx = fdl + (size_t)a.wp * PTS;
+    for (int i = tid; i < PTS && worker; i += NT) fx[i] = sX[pad_idx(i)];
+    if (TV) {
+      float2 *gx = irs + (size_t)a.wp2 * PTS;
+      for (int i = tid; i < PTS && worker; i += NT) gx[i] = sG[pad_idx(i)];
+    }
+  }
+
+  // ---- 2. spectral multiply-accumulate over this rank's partitions --------------------------------
+
+  if constexpr (PMAJOR) {
     // ---- a frame several times wider than the CTA: all tiles of a partition together, one accumulator per tile.
     // Register-fed (measured, 256 channels x 480000 taps: pts 1024 4.48 -> 6.36 TB/s, pts 2048 4.14 -> 4.65; pts 4096
     // (8 tiles) 4.09 -> 3.78, so the register-fed 8-tile case keeps the tile-by-tile sweep below) or TMA-fed -----
@@ -281,8 +299,7 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
         const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
 #pragma unroll
         for (int t = 0; t < TL; t++) {
-          const uint32_t s = slot % P::STAGES, round = slot / P::STAGES;
-          slot++;
+          const uint32_t s = slot % STAGES, round = slot / STAGES;
           if (!worker) {
             if ((tid & 31) == 0) {
               if (round > 0) tma::mbar_wait(bar_empty + 8 * s, (round - 1) & 1);  // consumers released the stage
@@ -303,6 +320,7 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
             __syncwarp();
             if ((tid & 31) == 0) tma::mbar_arrive(bar_empty + 8 * s);
           }
+          slot++;
         }
       }
       __syncwarp();  // the producer warp's lane 0 rejoins its warp before the next (aligned) barrier
@@ -379,9 +397,16 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
       }
       cluster.sync();  // remote reads done before anyone exits
     }
-    if (rank == 0 && worker) {
+    if (rank == 0) {
+      __syncthreads();  // the whole CTA is done with the new frames' spectra: Y takes their place in sX
+      if (worker) {
 #pragma unroll
-      for (int t = 0; t < TL; t++) sP[HALF + t * NT + tid] = acc[t];  // parked; moved to sX after the barrier below
+        for (int t = 0; t < TL; t++) {
+          const int q = t * NT + tid;
+          sX[pad_idx(2 * q)] = make_float2(acc[t].x, acc[t].y);
+          sX[pad_idx(2 * q + 1)] = make_float2(acc[t].z, acc[t].w);
+        }
+      }
     }
   } else
   for (int tile = 0; tile < P::TILES; tile++) {
@@ -398,7 +423,7 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
       const size_t frame_bytes = (size_t)PTS * sizeof(float2);
       for (int p = p_lo; p < p_hi; p++) {
         if (p == p_newx || p == p_newg) continue;
-        const uint32_t s = slot % P::STAGES, round = slot / P::STAGES;
+        const uint32_t s = slot % STAGES, round = slot / STAGES;
         slot++;
         if (!worker) {
           if ((tid & 31) == 0) {
@@ -495,16 +520,16 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
           sX[pad_idx(2 * q + 1)] = make_float2(acc.z, acc.w);
         } else {
           // park in the partial buffer area past the first HALF entries (sized for it by the host)
-          sP[HALF + q] = acc;
+          sPark[q] = acc;
         }
       }
     }
   }
   if (rank != 0) return;
   __syncthreads();
-  if (P::TILES > 1) {
+  if (P::TILES > 1 && !PMAJOR) {
     for (int q = tid; q < HALF && worker; q += NT) {
-      float4 y = sP[HALF + q];
+      float4 y = sPark[q];
       sX[pad_idx(2 * q)] = make_float2(y.x, y.y);
       sX[pad_idx(2 * q + 1)] = make_float2(y.z, y.w);
     }

@@ -79,6 +79,13 @@ if len(sys.argv) == 2 and sys.argv[1] == "--feed-sweep":
                 r = run(ch, 480000, pts, steps=20)
     eng.set_option("pconv_tma", -1)
     sys.exit(0)
+if len(sys.argv) == 2 and sys.argv[1] == "--wide":
+    # partitions wider than the CTA with the default feed, static and time-varying
+    for pts in (2048, 4096):
+        for ch in (64, 256, 1024):
+            for tv in (False, True):
+                run(ch, 480000, pts, steps=20, tv=tv)
+    sys.exit(0)
 if len(sys.argv) == 4:  # one configuration: channels ir_taps partition
     run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), steps=30)
     sys.exit(0)
