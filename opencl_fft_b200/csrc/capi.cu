@@ -978,11 +978,12 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   h->wp = 0;
   h->wp2 = h->nparts - 1;
   // Cluster split of the partitions (portable cluster limit 8), from measurements on B200 (tools/pconv_sweep.py
-  // --cluster-sweep, profiles/r02_pconv_cluster_sweep.txt). Partitions up to 1024 samples: enough CTAs for ~3.5 per SM
-  // (64 ch x 937 partitions: S=8 0.99 of the measured HBM peak vs 0.83 at S=4 and 0.36 at S=1; 128 ch: S=4 1.03 vs 0.97
-  // at S=2 -- the regime of the 8-GPU strong split; 256 ch x 187: S=2 0.97 vs 0.92). Longer partitions: one CTA per
-  // SM is enough and more only costs (256 ch x 4096: S=1 0.63, S=2 0.58, S=8 0.41). Many channels with long IRs: up
-  // to ~2048 CTAs while every CTA keeps >= 256 partitions to stream (1024 ch x 937: S=2 is 3 % faster than S=1 or 4).
+  // --cluster-sweep, profiles/r02_pconv_cluster_sweep.txt; fractions of the measured HBM peak). Partitions up to 1024
+  // samples: enough CTAs for ~3.5 per SM (64 ch x 937 partitions: S=8 0.98 vs 0.94 at S=4 and 0.47 at S=1; 128 ch:
+  // S=4 1.04 vs 1.02 at S=2 -- the regime of the 8-GPU strong split; 256 ch x 187: S=2 0.97 vs 0.96). Longer
+  // partitions: one CTA per SM-slot is enough and more only costs (256 ch x 4096: S=1 0.94, S=2 0.88, S=8 0.73; 64 ch x
+  // 4096: S=4 0.71, S=2 0.56, S=8 0.56). Many channels with long IRs: up to ~2048 CTAs while every CTA keeps >= 256
+  // partitions to stream (1024 ch x 937: S=2 is 3 % faster than S=1 or 4).
   int S = 1;
   const int target_ctas = pts <= 1024 ? 512 : 148;
   while (S < 8 && channels * S < target_ctas && S * 2 <= h->nparts) S *= 2;

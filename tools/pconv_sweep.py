@@ -64,7 +64,8 @@ if len(sys.argv) == 2 and sys.argv[1] == "--cluster-sweep":
     # choice of the cluster split (0) against every forced split
     for ch, cvs, pts in ((64, 96000, 512), (128, 96000, 512), (256, 96000, 512), (64, 480000, 512), (128, 480000, 512),
                          (256, 480000, 512), (512, 480000, 512), (256, 480000, 4096), (1024, 480000, 4096),
-                         (16, 480000, 2048), (64, 480000, 2048)):
+                         (16, 480000, 2048), (64, 480000, 2048), (128, 480000, 2048), (16, 480000, 4096), (64, 480000, 4096),
+                         (128, 480000, 4096)):
         for S in (0, 1, 2, 4, 8):
             eng.set_option("pconv_cluster", S)
             r = run(ch, cvs, pts, steps=30)
