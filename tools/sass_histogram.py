@@ -12,7 +12,7 @@ LIB = os.path.join(ROOT, "opencl_fft_b200", "lib", "libb200fft.so")
 want = [re.compile(a) for a in sys.argv[1:]] or [re.compile(
     r"fft_sm_kernel|pconv_step_kernel<9, false, false>|pconv_step_kernel<1[12], false, true>|pconv_mac_tma|"
     r"large_cols_kernel<7|large_rows_kernel<7, 8, false, true|cfft_kernel<1[02], false|rfft_fwd_reg_kernel<11|"
-    r"dconv_fir_kernel<16|pconv_push_ir_kernel<9")]
+    r"dconv_fir_kernel<16|pconv_push_ir_kernel<9|fft_thread_kernel<5|fft_thread_kernel<1, 0, false|rfft_fwd_reg_kernel<13")]
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
 KEYS = ["LDG.E.64", "LDG.E.128", "LDG.E (32)", "STG.E.64", "STG.E.128", "STG.E (32)", "LDS.64", "LDS.128", "STS.64", "STS.128",
