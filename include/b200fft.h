@@ -72,6 +72,8 @@ const char *b2f_version(void);
  *                            channels), FFT batches above 1 MB (eight chunks of the batch)
  *   zerocopy_max      65536  host calls moving at most this many bytes run on pinned buffers directly
  *   graph             1      CUDA graph replay for the multi-launch host paths (pts >= 8192)
+ *   pinned_direct     1      partitioned-convolution host calls above zerocopy_max whose buffers the caller has
+ *                            page-locked: one launch reads / writes them in place over PCIe (no staging copies)
  *   fft_prefetch      -1     real transforms of 8192 / 16384 complex points, one CTA each: L2 prefetch of the
  *                            transform this many CTAs ahead (-1: the co-resident CTAs, 0: off)
  *   verbose           0

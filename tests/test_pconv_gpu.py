@@ -298,6 +298,42 @@ def test_pipelined_host_call_equals_device_path(eng, options):
         assert np.array_equal(d_y.cpu().numpy(), y_pipe[t])
 
 
+@pytest.mark.parametrize("tv", [False, True])
+def test_caller_pinned_buffers_run_in_place(eng, options, tv):
+    """Host calls above the bounce-buffer size on buffers the CALLER has page-locked: one launch reads the input blocks
+    from and writes the output blocks to that memory directly (option pinned_direct). Same bits as the staged form
+    (pageable buffers, and pinned ones with the option off), static and time-varying, delay line wrapped."""
+    import torch
+
+    pts, nparts, channels, nb = 512, 5, 600, 12
+    rng = np.random.default_rng(12)
+    ir = (rng.standard_normal((channels, pts * nparts)) * 0.05).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, channels, pts)).astype(np.float32)
+    x2 = (rng.standard_normal((nb, channels, pts)) * 0.05).astype(np.float32)
+
+    def run(pinned):
+        c = eng.Clpconv(0, pts * nparts, pts, channels=channels)
+        if not tv:
+            assert c.push_ir(ir.reshape(-1)) == 0
+        if pinned:
+            hx, hx2, hy = (torch.empty(channels, pts).pin_memory().numpy() for _ in range(3))
+        else:
+            hx, hx2, hy = (np.empty((channels, pts), np.float32) for _ in range(3))
+        ys = []
+        for t in range(nb):
+            hx[:], hx2[:] = x[t], x2[t]
+            assert (c.convolution(hy, hx, hx2) if tv else c.convolution(hy, hx)) == 0
+            ys.append(hy.copy())
+        return np.stack(ys)
+
+    y_direct = run(True)
+    y_pageable = run(False)
+    options("pinned_direct", 0)
+    y_staged = run(True)
+    assert np.array_equal(y_direct, y_pageable) and np.array_equal(y_direct, y_staged)
+    assert np.abs(y_direct).max() > 0
+
+
 def test_benched_launch_configuration_vs_oracle(eng, port):
     """The exact configuration bench.py times (BASELINE configs[4]): 1024 channels x 480000 taps x 512-sample
     partitions = 937 partitions, which selects 2-CTA clusters. Four scattered channels against the oracle over three
