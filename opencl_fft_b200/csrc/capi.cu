@@ -411,8 +411,24 @@ struct SmPlan {
     if (rc) return rc;
     const int units = (batch + (32 >> LOG1) - 1) / (32 >> LOG1);
     const int g = units < grid ? units : grid;
+#if B2F_SMX_PDL
+    // programmatic dependent launch: scheduled while the stream's previous kernel drains (see the kernel's prologue)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g);
+    cfg.blockDim = dim3(SmGeom::THREADS);
+    cfg.dynamicSmemBytes = SmGeom::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const float2 *a_twn = d_twn, *a_twp = d_twp, *a_twa = d_twa;
+    CK(cudaLaunchKernelEx(&cfg, kern, in, out, a_twn, a_twp, a_twa, hw, batch, scale));
+#else
     kern<<<g, SmGeom::THREADS, SmGeom::SMEM, st>>>(in, out, d_twn, d_twp, d_twa, hw, batch, scale);
     CK(cudaGetLastError());
+#endif
     return B2F_OK;
   }
   template <bool INV, int KIND>

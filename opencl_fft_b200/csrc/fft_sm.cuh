@@ -49,6 +49,13 @@
 #define B2F_SMX_FFT(x) x
 #endif
 
+#ifndef B2F_SMX_PDL
+#define B2F_SMX_PDL 1
+#endif
+#ifndef B2F_SMX_FIRST_PF
+#define B2F_SMX_FIRST_PF 1
+#endif
+
 namespace b2f {
 
 // v[m] *= W^m for m = 1..31, given W^1, W^2, W^4, W^8, W^16 (base[b] = W^(2^b)): the other 26 powers are products
@@ -219,6 +226,12 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   uint32_t *misc = reinterpret_cast<uint32_t *>(smraw + G::OFF_MISC);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+#if B2F_SMX_PDL
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled from now on (its CTAs become
+  // resident as ours exit and run their set-up); it reads and writes nothing the stream's earlier kernels touch
+  // before its own griddepcontrol.wait below, which returns when those have completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
   if (tid < 5 * 32) {
     twn[tid] = __ldg(&twn_g[tid]);
     twp[tid] = __ldg(&twp_g[tid]);
@@ -277,7 +290,19 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
     tma::fence_barrier_init();
   }
   __syncthreads();
-  if (warp == 0) stage_round(0, blockIdx.x);
+#if B2F_SMX_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+  if (warp == 0) {
+    stage_round(0, blockIdx.x);
+#if B2F_SMX_FIRST_PF
+    {  // the first unit's round 1 starts towards L2 together with round 0 (later units: during the previous unit's job 1)
+      int tr = blockIdx.x * NTR + lane / N1;
+      tr = tr < batch ? tr : batch - 1;
+      tma::prefetch_l2(in + (size_t)tr * N + 1024 * (lane % N1) + 512, 4096);
+    }
+#endif
+  }
   uint32_t par = 0;
 
   for (int t = blockIdx.x; t < units; t += gridDim.x, par ^= 1) {
