@@ -76,6 +76,8 @@ const char *b2f_version(void);
  *                            page-locked: one launch reads / writes them in place over PCIe (no staging copies)
  *   fft_prefetch      -1     real transforms of 8192 / 16384 complex points, one CTA each: L2 prefetch of the
  *                            transform this many CTAs ahead (-1: the co-resident CTAs, 0: off)
+ *   pconv_push_reg    1      push_ir (64 <= pts <= 4096) on the register-level real transform of the batched FFT;
+ *                            0: the step kernel's frame routine (shared-memory split)
  *   verbose           0
  * Unknown names return B2F_ERR_INVALID_VALUE. */
 int b2f_set_option(const char *name, long long value);

@@ -76,6 +76,7 @@ struct Options {
   long long graph = 1;               // CUDA graph for the multi-launch host paths
   long long pinned_direct = 1;       // pconv host calls on caller-pinned buffers: the kernel reads / writes them in place
   long long fft_prefetch = -1;       // real one-CTA transforms of N >= 8192: L2 prefetch distance in CTAs (-1: the resident CTAs, 0: off)
+  long long pconv_push_reg = 1;      // push_ir on the register-level real transform (pts >= 64); 0: the step kernel's frame routine
   long long verbose = 0;
 };
 struct OptionName {
@@ -94,6 +95,7 @@ static const OptionName kOptionNames[] = {
     {"graph", "B2F_GRAPH", &Options::graph},
     {"pinned_direct", "B2F_PINNED_DIRECT", &Options::pinned_direct},
     {"fft_prefetch", "B2F_FFT_PREFETCH", &Options::fft_prefetch},
+    {"pconv_push_reg", "B2F_PCONV_PUSH_REG", &Options::pconv_push_reg},
     {"verbose", "B2F_VERBOSE", &Options::verbose},
 };
 static std::mutex g_opt_mutex;
@@ -856,6 +858,7 @@ struct b2f_pconv {
   int device = 0, cvs = 0, pts = 0, logp = 0, nparts = 0, channels = 1;
   int wp = 0, wp2 = 0;  // ring positions, cl_conv.cpp:144
   float2 *d_fdl = nullptr, *d_irs = nullptr, *d_tw = nullptr, *d_w2 = nullptr;
+  float2 *d_hw = nullptr;   // folded split table 0.5 i w2 (push_ir's register-level transform, pts >= 64)
   float *d_tail = nullptr, *d_in1 = nullptr, *d_in2 = nullptr, *d_out = nullptr, *d_ir = nullptr;
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second half of the channels in the pipelined host call
   Staging sg_in, sg_in2, sg_out;
@@ -875,8 +878,8 @@ struct b2f_pconv {
     DeviceGuard guard(device);  // a failed create may carry an invalid ordinal: the guard swallows that
     for (cudaGraphExec_t g : graph)
       if (g) cudaGraphExecDestroy(g);
-    for (void *p : {(void *)d_fdl, (void *)d_irs, (void *)d_tw, (void *)d_w2, (void *)d_tail, (void *)d_in1,
-                    (void *)d_in2, (void *)d_out, (void *)d_ir, (void *)d_pad, (void *)d_Y, (void *)d_state})
+    for (void *p : {(void *)d_fdl, (void *)d_irs, (void *)d_tw, (void *)d_w2, (void *)d_hw, (void *)d_tail,
+                    (void *)d_in1, (void *)d_in2, (void *)d_out, (void *)d_ir, (void *)d_pad, (void *)d_Y, (void *)d_state})
       if (p) cudaFree(p);
     for (FftPlanCore *p : {gfwd, ginv})
       if (p) {
@@ -935,12 +938,22 @@ static int launch_pconv_step_t(const PconvArgs &a, int channels, int S, int tma_
 }
 template <int LOGP>
 static int launch_pconv_push_t(const float *ir, size_t stride, b2f_pconv *h, cudaStream_t st) {
-  using P = PconvGeom<LOGP>;
-  const int smem = (P::FFT_SMEM + 1) * (int)sizeof(float2);
-  int rc = set_smem(pconv_push_ir_kernel<LOGP>, smem);
+  if constexpr (RegSplitGeom<LOGP>::OK) {
+    if (h->opt.pconv_push_reg) {
+      using B = BatchGeom<LOGP>;
+      int rc = set_smem(pconv_push_ir_reg_kernel<LOGP>, B::SMEM_BYTES);
+      if (rc) return rc;
+      dim3 grid((h->nparts + B::TPB - 1) / B::TPB, h->channels, 1);
+      pconv_push_ir_reg_kernel<LOGP><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(ir, stride, h->d_irs, h->d_tw, h->d_hw, h->nparts, h->wp2);
+      CK(cudaGetLastError());
+      return B2F_OK;
+    }
+  }
+  using Q = PushGeom<LOGP>;
+  int rc = set_smem(pconv_push_ir_kernel<LOGP>, Q::SMEM_BYTES);
   if (rc) return rc;
-  dim3 grid(h->nparts, h->channels, 1);
-  pconv_push_ir_kernel<LOGP><<<grid, P::FT, smem, st>>>(ir, stride, h->d_irs, h->d_tw, h->d_w2, h->nparts, h->wp2);
+  dim3 grid((h->nparts + Q::GROUPS - 1) / Q::GROUPS, h->channels, 1);
+  pconv_push_ir_kernel<LOGP><<<grid, Q::THREADS, Q::SMEM_BYTES, st>>>(ir, stride, h->d_irs, h->d_tw, h->d_w2, h->nparts, h->wp2);
   CK(cudaGetLastError());
   return B2F_OK;
 }
@@ -1022,6 +1035,12 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   if (logp <= kPconvMaxLogP) {
     if ((rc = upload(make_pass_twiddles(logp), &h->d_tw))) return fail(rc);
     if ((rc = upload(make_split_twiddles(pts), &h->d_w2))) return fail(rc);
+    {
+      const std::vector<float2> w2 = make_split_twiddles(pts);
+      std::vector<float2> hw((size_t)pts / 2 + 1);
+      for (int i = 0; i <= pts / 2 && i < pts; i++) hw[i] = make_float2(-0.5f * w2[i].y, 0.5f * w2[i].x);  // 0.5 i w2[i]
+      if ((rc = upload(hw, &h->d_hw))) return fail(rc);
+    }
   } else {
     h->gfwd = new (std::nothrow) FftPlanCore;
     h->ginv = new (std::nothrow) FftPlanCore;

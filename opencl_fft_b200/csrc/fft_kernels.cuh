@@ -110,22 +110,24 @@ struct RegSplitGeom {
 };
 
 // forward: in [batch][2N] float, out [batch][N] float2 (may alias). hw: folded table (scale included).
-template <int LOGN>
-__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
-    rfft_fwd_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
-                        int batch, float scale, int ahead) {
+// ZEROPAD (Clpconv::push_ir, cl_conv.cpp:361-380): the transform's input is N reals followed by N zeros -- only the
+// first N/2 packed elements are read, and they may be 4-byte aligned only (`pair_ok` false).
+template <int LOGN, bool ZEROPAD>
+__device__ __forceinline__ void rfft_fwd_reg_body(const float2 *src, float2 *dst, bool active, bool pair_ok, float2 *sm,
+                                                  const float2 *__restrict__ tw, const float2 *__restrict__ hw, int t,
+                                                  float scale) {
   using B = BatchGeom<LOGN>;
   constexpr int N = 1 << LOGN, T = B::T, E = FftGeom<LOGN>::E, H = E / 2;
-  extern __shared__ float2 smem[];
-  const int lt = threadIdx.x / T, t = threadIdx.x % T;
-  const long long b = (long long)blockIdx.x * B::TPB + lt;
-  const bool active = b < batch;
-  const float2 *src = in + (active ? b : 0) * N;
-  float2 *dst = out + (active ? b : 0) * N;
-  float2 *sm = smem + lt * BatchGeom<LOGN>::ROW;
   float2 x[E];
-  prefetch_successor<LOGN>(in, ahead, batch);
-  auto load = [&](int idx, int) { return active ? __ldcs(src + idx) : make_float2(0.f, 0.f); };
+  auto load = [&](int idx, int) {
+    if constexpr (ZEROPAD) {
+      if (!active || idx >= N / 2) return make_float2(0.f, 0.f);
+      const float *xr = reinterpret_cast<const float *>(src);
+      return pair_ok ? __ldcs(src + idx) : make_float2(__ldcs(xr + 2 * idx), __ldcs(xr + 2 * idx + 1));
+    } else {
+      return active ? __ldcs(src + idx) : make_float2(0.f, 0.f);
+    }
+  };
   auto store = [&](int, float2 v, int slot) { x[slot] = v; };  // last pass: slot == m, value X[t + m*T]
   fft_run<LOGN, false>(load, store, sm, tw, t, CtaSync());
   __syncthreads();  // every thread is past its last gather: sm becomes the staging area [E/2][T]
@@ -152,6 +154,20 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
     __stcs(dst + t + m * T, a);
     __stcs(dst + pt + pm * T, bb);
   }
+}
+template <int LOGN>
+__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
+    rfft_fwd_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
+                        int batch, float scale, int ahead) {
+  using B = BatchGeom<LOGN>;
+  constexpr int N = 1 << LOGN, T = B::T;
+  extern __shared__ float2 smem[];
+  const int lt = threadIdx.x / T, t = threadIdx.x % T;
+  const long long b = (long long)blockIdx.x * B::TPB + lt;
+  const bool active = b < batch;
+  prefetch_successor<LOGN>(in, ahead, batch);
+  rfft_fwd_reg_body<LOGN, false>(in + (active ? b : 0) * N, out + (active ? b : 0) * N, active, true,
+                                 smem + lt * BatchGeom<LOGN>::ROW, tw, hw, t, scale);
 }
 
 // inverse: in [batch][N] float2, out [batch][2N] float (may alias). hw: folded inverse table.

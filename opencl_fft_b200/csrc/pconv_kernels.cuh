@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include "fft_core.cuh"
+#include "fft_kernels.cuh"
 #include "tma_utils.cuh"
 
 namespace b2f {
@@ -569,25 +570,95 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
 }
 
 // IR partition transform (Clpconv::push_ir, cl_conv.cpp:353-388), all partitions of all channels in
-// one launch. grid = (nparts, channels), CTA = the FT threads that carry one frame's FFT (one warp for pts <= 512):
-// small CTAs, up to 32 of them per SM, instead of step-kernel-sized CTAs in which only the FFT group works
-// (1024 x 937 partitions of 512: 4.0 -> 1.5 ms, 3.9 TB/s). Partition i goes to IR frame (wp2 - i) mod nparts.
+// one launch. A frame is carried by the FT threads of its FFT (one warp for pts <= 512); a CTA holds GROUPS such
+// groups (256 threads in all), each with its own frame, shared-memory buffer and NAMED barrier, so the groups never
+// wait for each other. History, 1024 x 937 partitions of 512: step-kernel-sized CTAs in which only the FFT group
+// works 4.0 ms; one 32-thread CTA per frame 1.53 ms (3.9 TB/s); eight frames per 256-thread CTA, this kernel: 1.53 ms
+// again -- not the CTA start rate but the four shared-memory passes over every frame (transform, split in place,
+// copy out) bound it. pts >= 64 therefore runs pconv_push_ir_reg_kernel below (1.22 ms, 4.8 TB/s; pts 128: 0.83 ->
+// 0.26 ms); this kernel serves pts < 64 and the `pconv_push_reg` = 0 comparison. Partition i goes to IR frame
+// (wp2 - i) mod nparts. The arithmetic is that of pconv_forward_frame, instruction for instruction.
 template <int LOGP>
-__global__ void __launch_bounds__(PconvGeom<LOGP>::FT)
+struct PushGeom {
+  using P = PconvGeom<LOGP>;
+  static constexpr int GROUPS = P::FT >= 256 ? 1 : 256 / P::FT;
+  static constexpr int THREADS = GROUPS * P::FT;
+  static constexpr int GROUP_F2 = P::FFT_SMEM + (P::FFT_SMEM & 1) + 2;  // float2 per group buffer (16-byte multiple)
+  static constexpr int SMEM_BYTES = GROUPS * GROUP_F2 * (int)sizeof(float2);
+};
+// barrier `id` (1..15) over COUNT threads
+template <int COUNT>
+struct NamedGroupSync {
+  int id;
+  __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory"); }
+};
+template <int LOGP>
+__global__ void __launch_bounds__(PushGeom<LOGP>::THREADS)
     pconv_push_ir_kernel(const float *ir, size_t ir_stride, float2 *irs, const float2 *__restrict__ tw,
                          const float2 *__restrict__ w2, int nparts, int wp2) {
   using P = PconvGeom<LOGP>;
-  constexpr int PTS = P::PTS;
+  using Q = PushGeom<LOGP>;
+  constexpr int PTS = P::PTS, N = PTS, FT = P::FT;
   extern __shared__ float4 smem4[];
-  float2 *sX = reinterpret_cast<float2 *>(smem4);
-  const int i = blockIdx.x, ch = blockIdx.y;
-  pconv_forward_frame<LOGP, P::FT>(ir + (size_t)ch * ir_stride + (size_t)i * PTS, sX, tw, w2);
+  const int grp = threadIdx.x / FT, gt = threadIdx.x % FT;
+  const int i = blockIdx.x * Q::GROUPS + grp, ch = blockIdx.y;
+  if (i >= nparts) return;  // whole groups leave: nobody else waits on their barrier
+  float2 *sm = reinterpret_cast<float2 *>(smem4) + grp * Q::GROUP_F2;
+  const NamedGroupSync<FT> sync{grp + 1};
+  const float *x = ir + (size_t)ch * ir_stride + (size_t)i * PTS;
+  {
+    const int vt = gt / P::T, t = gt % P::T;
+    float2 *my = sm + vt * FftGeom<LOGP>::SMEM;
+    const bool real = (vt == 0);
+    // an IR pushed with an odd channel stride (push_ir_dev) leaves rows that are only 4-byte aligned
+    const bool pair_ok = (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+    auto load = [&](int idx, int) {
+      if (real && idx < N / 2)
+        return pair_ok ? *reinterpret_cast<const float2 *>(x + 2 * idx) : make_float2(x[2 * idx], x[2 * idx + 1]);
+      return make_float2(0.f, 0.f);
+    };
+    auto store = [&](int idx, float2 v, int) { my[pad_idx(idx)] = v; };
+    fft_run<LOGP, false, true>(load, store, my, tw, t, sync);
+  }
+  sync();
+  for (int k = gt; k < N / 2; k += FT) {
+    if (k == 0) {
+      sm[pad_idx(0)] = rfft_dc<false>(sm[pad_idx(0)]);
+    } else {
+      float2 ci = sm[pad_idx(k)], cj = sm[pad_idx(N - k)];
+      rfft_pair<false>(ci, cj, __ldg(&w2[k]));
+      sm[pad_idx(k)] = ci;
+      sm[pad_idx(N - k)] = cj;
+    }
+  }
+  sync();
   int frame = (wp2 - i) % nparts;
   if (frame < 0) frame += nparts;
   float2 *g = irs + ((size_t)ch * nparts + frame) * PTS;
-  for (int k = threadIdx.x; k < PTS; k += P::FT) g[k] = sX[pad_idx(k)];
+  for (int k = gt; k < PTS; k += FT) g[k] = sm[pad_idx(k)];
 }
 
+
+// pts >= 64: the same frames on the register-level real transform of the batched FFT (fft_kernels.cuh: split in
+// registers with the folded table, one shared-memory exchange instead of four passes over the frame), reading the
+// pts reals of a partition as the first half of a zero-padded 2 pts-point input and writing to the partition's ring
+// frame. grid = (ceil(nparts / TPB), channels). hw: folded split table of the pts-point plan, scale 1.
+template <int LOGP>
+__global__ void __launch_bounds__(BatchGeom<LOGP>::THREADS, BatchGeom<LOGP>::MIN_BLOCKS)
+    pconv_push_ir_reg_kernel(const float *ir, size_t ir_stride, float2 *irs, const float2 *__restrict__ tw,
+                             const float2 *__restrict__ hw, int nparts, int wp2) {
+  using B = BatchGeom<LOGP>;
+  constexpr int PTS = 1 << LOGP, T = B::T;
+  extern __shared__ float2 smem_push[];
+  const int lt = threadIdx.x / T, t = threadIdx.x % T;
+  const int i = blockIdx.x * B::TPB + lt, ch = blockIdx.y;
+  const bool active = i < nparts;
+  const float *x = ir + (size_t)ch * ir_stride + (size_t)(active ? i : 0) * PTS;
+  int frame = (wp2 - (active ? i : 0)) % nparts;
+  if (frame < 0) frame += nparts;
+  rfft_fwd_reg_body<LOGP, true>(reinterpret_cast<const float2 *>(x), irs + ((size_t)ch * nparts + frame) * PTS, active,
+                                (reinterpret_cast<uintptr_t>(x) & 7) == 0, smem_push + lt * B::ROW, tw, hw, t, 1.0f);
+}
 
 // =====================================================================================================
 // General path for partitions too long for the fused kernel (pts = 8192 .. 32768, the upper half of the
