@@ -66,7 +66,7 @@ const char *b2f_version(void);
  *   rows_rb16         0      16-row CTAs in the four-step real rows kernel
  *   separate_split    0      unfused real split / unsplit pass on the four-step path
  *   pconv_tma         -1     partitioned-convolution MAC feed: -1 measured choice, 0 registers, 1 TMA
- *   pconv_cluster     0      cluster split of the partitions: 0 measured choice, else 1 | 2 | 4 | 8
+ *   pconv_cluster     0      cluster split of the partitions: 0 measured choice, else 1 | 2 | 4 | 8 | 16
  *                            (anything else, or more than nparts: create fails with INVALID_VALUE)
  *   pconv_pipeline    1      two-stream host calls: partitioned convolution with >= 128 channels (halves of the
  *                            channels), FFT batches above 1 MB (eight chunks of the batch)
@@ -76,6 +76,8 @@ const char *b2f_version(void);
  *                            page-locked: one launch reads / writes them in place over PCIe (no staging copies)
  *   fft_prefetch      -1     real transforms of 8192 / 16384 complex points, one CTA each: L2 prefetch of the
  *                            transform this many CTAs ahead (-1: the co-resident CTAs, 0: off)
+ *   pconv_cluster16_max_channels 4  clusters of 16 CTAs (non-portable size) for handles of up to this many channels
+ *                            and at least 8 MB of rings per channel; 0 never
  *   pconv_push_reg    1      push_ir (64 <= pts <= 4096) on the register-level real transform of the batched FFT;
  *                            0: the step kernel's frame routine (shared-memory split)
  *   verbose           0

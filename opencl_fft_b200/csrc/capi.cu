@@ -76,6 +76,7 @@ struct Options {
   long long graph = 1;               // CUDA graph for the multi-launch host paths
   long long pinned_direct = 1;       // pconv host calls on caller-pinned buffers: the kernel reads / writes them in place
   long long fft_prefetch = -1;       // real one-CTA transforms of N >= 8192: L2 prefetch distance in CTAs (-1: the resident CTAs, 0: off)
+  long long pconv_cluster16_max_channels = 4;  // clusters of 16 CTAs for up to this many channels with long IRs (0: never)
   long long pconv_push_reg = 1;      // push_ir on the register-level real transform (pts >= 64); 0: the step kernel's frame routine
   long long verbose = 0;
 };
@@ -95,6 +96,7 @@ static const OptionName kOptionNames[] = {
     {"graph", "B2F_GRAPH", &Options::graph},
     {"pinned_direct", "B2F_PINNED_DIRECT", &Options::pinned_direct},
     {"fft_prefetch", "B2F_FFT_PREFETCH", &Options::fft_prefetch},
+    {"pconv_cluster16_max_channels", "B2F_PCONV_CLUSTER16_MAX_CHANNELS", &Options::pconv_cluster16_max_channels},
     {"pconv_push_reg", "B2F_PCONV_PUSH_REG", &Options::pconv_push_reg},
     {"verbose", "B2F_VERBOSE", &Options::verbose},
 };
@@ -247,6 +249,20 @@ static int set_smem_once(const void *fn, int bytes) {
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   std::lock_guard<std::mutex> lk(m);
   done[key] = bytes;
+  return B2F_OK;
+}
+// Clusters of 16 CTAs are beyond the portable limit of 8: opt the kernel in, once per (kernel, device)
+static int allow_cluster16_once(const void *fn) {
+  static std::mutex m;
+  static std::unordered_map<uint64_t, int> done;
+  const uint64_t key = (uint64_t)(uintptr_t)fn * 64u + (uint64_t)(g_device < 0 ? 63 : g_device & 63);
+  {
+    std::lock_guard<std::mutex> lk(m);
+    if (done.count(key)) return B2F_OK;
+  }
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  std::lock_guard<std::mutex> lk(m);
+  done[key] = 1;
   return B2F_OK;
 }
 template <class K>
@@ -909,6 +925,7 @@ static int launch_pconv_step_tt(const PconvArgs &a, int channels, int S, cudaStr
   const int smem = pconv_smem_bytes<LOGP>(TV, TMA, S);
   int rc = set_smem(pconv_step_kernel<LOGP, TV, TMA>, smem);
   if (rc) return rc;
+  if (S > 8 && (rc = allow_cluster16_once((const void *)pconv_step_kernel<LOGP, TV, TMA>))) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(S, channels, 1);
   cfg.blockDim = dim3(P::NTHREADS + (TMA ? 32 : 0), 1, 1);
@@ -1019,6 +1036,12 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   const int target_ctas = pts <= 1024 ? 512 : 148;
   while (S < 8 && channels * S < target_ctas && S * 2 <= h->nparts) S *= 2;
   while (S < 8 && channels * S < 2048 && h->nparts / (2 * S) >= 256) S *= 2;
+  // A handful of channels with a long IR (the mono rows of csound/tests.py's grid): every CTA streams at what ONE SM
+  // can pull (~60-100 GB/s), so the step time is nparts / S; a cluster of 16 (beyond the portable limit, one per GPC
+  // at a time) halves it once more.
+  // Measured, mono (tools/rt_ratio_grid.py): pts 512 x 8192 partitions 147 -> 82 us per block, pts 2048 x 2048: 256 -> 136;
+  // nothing to gain below ~8 MB of rings per channel (pts 512 x 1024: 31.0 vs 29.5 us).
+  if (S == 8 && channels <= h->opt.pconv_cluster16_max_channels && (long long)h->nparts * pts >= (1 << 19) && h->nparts >= 64) S = 16;
   auto fail = [&](int code) {
     h->destroy();
     delete h;
@@ -1026,7 +1049,7 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   };
   if (h->opt.pconv_cluster) {  // forced split: a power of two within the portable cluster size, at most one CTA per partition
     const long long f = h->opt.pconv_cluster;
-    if ((f != 1 && f != 2 && f != 4 && f != 8) || f > h->nparts) return fail(B2F_ERR_INVALID_VALUE);
+    if ((f != 1 && f != 2 && f != 4 && f != 8 && f != 16) || f > h->nparts) return fail(B2F_ERR_INVALID_VALUE);
     S = (int)f;
   }
   h->cluster = S;

@@ -360,9 +360,9 @@ def test_benched_launch_configuration_vs_oracle(eng, port):
         assert rel_l2(y[:, k].cpu().numpy(), want) < TOL, k
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
 def test_ring_wrap_for_every_cluster_size(eng, port, options, cluster):
-    """40 partitions split over clusters of 1 / 2 / 4 / 8 CTAs (option pconv_cluster), 2 * nparts + 2 blocks so that the
+    """40 partitions split over clusters of 1 / 2 / 4 / 8 / 16 CTAs (option pconv_cluster), 2 * nparts + 2 blocks so that the
     delay line wraps twice, static and time-varying, against the oracle."""
     options("pconv_cluster", cluster)
     pts, nparts, channels = 512, 40, 3
@@ -391,7 +391,7 @@ def test_invalid_cluster_option_is_rejected_at_create(eng, options):
     assert eng.Clpconv(0, 4 * 512, 512, uData=1).get_cl_err() == 2  # more CTAs than partitions
 
 
-@pytest.mark.parametrize("pts,channels", [(8192, 2), (32768, 1)])
+@pytest.mark.parametrize("pts,channels", [(8192, 2), (32768, 1), (32768, 100)])  # 100 channels: the one-SM FFT kernel (programmatic dependent launch) inside the graph
 def test_graph_replay_equals_stream_launches(eng, port, options, pts, channels):
     """General path (pts >= 8192, 7-9 launches per block): the host call replays the block as one CUDA graph over
     device-resident ring positions. Same bits as the plain stream launches (option graph = 0), static and
