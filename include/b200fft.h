@@ -78,6 +78,13 @@ const char *b2f_version(void);
  *                            transform this many CTAs ahead (-1: the co-resident CTAs, 0: off)
  *   pconv_cluster16_max_channels 4  clusters of 16 CTAs (non-portable size) for handles of up to this many channels
  *                            and at least 8 MB of rings per channel; 0 never
+ *   pconv_deep_ring   1      handles whose launches put at most one CTA on an SM and whose CTAs stream >= 96 partitions
+ *                            of 2048 / 4096 samples each (mono, long IR): TMA stages of 32 KB; 0: the usual 4 KB slices
+ *   pconv_ksplit      0      pts >= 8192 with few channels: the partitions of the spectral multiply-accumulate are split
+ *                            over this many CTAs per 512-bin tile and the partial sums added by a second launch
+ *                            (0: enough for two CTAs per SM, -1: never)
+ *   pconv_general_fused 1    pts 8192 / 16384 below the one-SM FFT's batch: a block is new frames -> multiply-accumulate
+ *                            (-> partial sums) -> inverse transform + overlap-add, 3-4 launches; 0: the 11-12 separate ones
  *   pconv_push_reg    1      push_ir (64 <= pts <= 4096) on the register-level real transform of the batched FFT;
  *                            0: the step kernel's frame routine (shared-memory split)
  *   verbose           0

@@ -77,6 +77,9 @@ struct Options {
   long long pinned_direct = 1;       // pconv host calls on caller-pinned buffers: the kernel reads / writes them in place
   long long fft_prefetch = -1;       // real one-CTA transforms of N >= 8192: L2 prefetch distance in CTAs (-1: the resident CTAs, 0: off)
   long long pconv_cluster16_max_channels = 4;  // clusters of 16 CTAs for up to this many channels with long IRs (0: never)
+  long long pconv_deep_ring = 1;     // launches of at most one CTA per SM streaming >= 96 partitions each (pts 2048 / 4096): TMA stages of 32 KB
+  long long pconv_ksplit = 0;        // general path (pts >= 8192): partitions split over this many CTAs per tile (0: measured choice, -1: never)
+  long long pconv_general_fused = 1; // pts 8192 / 16384: frames and inverse + overlap-add as fused launches (0: pad / rFFT / copy / ... one by one)
   long long pconv_push_reg = 1;      // push_ir on the register-level real transform (pts >= 64); 0: the step kernel's frame routine
   long long verbose = 0;
 };
@@ -97,6 +100,9 @@ static const OptionName kOptionNames[] = {
     {"pinned_direct", "B2F_PINNED_DIRECT", &Options::pinned_direct},
     {"fft_prefetch", "B2F_FFT_PREFETCH", &Options::fft_prefetch},
     {"pconv_cluster16_max_channels", "B2F_PCONV_CLUSTER16_MAX_CHANNELS", &Options::pconv_cluster16_max_channels},
+    {"pconv_deep_ring", "B2F_PCONV_DEEP_RING", &Options::pconv_deep_ring},
+    {"pconv_ksplit", "B2F_PCONV_KSPLIT", &Options::pconv_ksplit},
+    {"pconv_general_fused", "B2F_PCONV_GENERAL_FUSED", &Options::pconv_general_fused},
     {"pconv_push_reg", "B2F_PCONV_PUSH_REG", &Options::pconv_push_reg},
     {"verbose", "B2F_VERBOSE", &Options::verbose},
 };
@@ -879,6 +885,7 @@ struct b2f_pconv {
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second half of the channels in the pipelined host call
   Staging sg_in, sg_in2, sg_out;
   int cluster = 1;
+  bool deep = false;        // whole-handle launches have at most one CTA per SM: TMA feed with the deep ring
   Options opt;
   int failed = 0;           // sticky: a multi-stream host call broke off half way, the state is not trustworthy
   // general path (pts > 2^kPconvMaxLogP): batched real-FFT plans + pad / MAC / overlap-add kernels; ring positions in
@@ -886,6 +893,8 @@ struct b2f_pconv {
   FftPlanCore *gfwd = nullptr, *ginv = nullptr;
   float *d_pad = nullptr;   // [channels][2*pts]
   float2 *d_Y = nullptr;    // [channels][pts]
+  float2 *d_Ypart = nullptr;  // [ksplit][channels][pts]: partial sums of a MAC whose partitions are split over CTAs
+  int ksplit = 1;
   int *d_state = nullptr;   // {wp, wp2}
   cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [time-varying]: H2D, the block's launches, D2H on fixed buffers
   bool general() const { return gfwd != nullptr; }
@@ -895,7 +904,7 @@ struct b2f_pconv {
     for (cudaGraphExec_t g : graph)
       if (g) cudaGraphExecDestroy(g);
     for (void *p : {(void *)d_fdl, (void *)d_irs, (void *)d_tw, (void *)d_w2, (void *)d_hw, (void *)d_tail,
-                    (void *)d_in1, (void *)d_in2, (void *)d_out, (void *)d_ir, (void *)d_pad, (void *)d_Y, (void *)d_state})
+                    (void *)d_in1, (void *)d_in2, (void *)d_out, (void *)d_ir, (void *)d_pad, (void *)d_Y, (void *)d_Ypart, (void *)d_state})
       if (p) cudaFree(p);
     for (FftPlanCore *p : {gfwd, ginv})
       if (p) {
@@ -911,21 +920,21 @@ struct b2f_pconv {
 };
 
 template <int LOGP>
-static int pconv_smem_bytes(bool tv, bool tma, int S) {
+static int pconv_smem_bytes(bool tv, bool tma, int S, bool deep = false) {
   using P = PconvGeom<LOGP>;
   const int fft = P::FFT_SMEM + (P::FFT_SMEM & 1);
   const int partial4 = P::partial_f4(tma, S);
-  const int ring = tma ? P::ring_f4(tv) * (int)sizeof(float4) + 2 * P::stages(tv) * 8 : 0;
+  const int ring = tma ? P::ring_f4(deep) * (int)sizeof(float4) + 2 * P::stages(deep) * 8 : 0;
   return (tv ? 2 : 1) * fft * (int)sizeof(float2) + partial4 * (int)sizeof(float4) + ring;
 }
 
-template <int LOGP, bool TV, bool TMA>
+template <int LOGP, bool TV, bool TMA, bool DEEP = false>
 static int launch_pconv_step_tt(const PconvArgs &a, int channels, int S, cudaStream_t st) {
   using P = PconvGeom<LOGP>;
-  const int smem = pconv_smem_bytes<LOGP>(TV, TMA, S);
-  int rc = set_smem(pconv_step_kernel<LOGP, TV, TMA>, smem);
+  const int smem = pconv_smem_bytes<LOGP>(TV, TMA, S, DEEP);
+  int rc = set_smem(pconv_step_kernel<LOGP, TV, TMA, DEEP>, smem);
   if (rc) return rc;
-  if (S > 8 && (rc = allow_cluster16_once((const void *)pconv_step_kernel<LOGP, TV, TMA>))) return rc;
+  if (S > 8 && (rc = allow_cluster16_once((const void *)pconv_step_kernel<LOGP, TV, TMA, DEEP>))) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(S, channels, 1);
   cfg.blockDim = dim3(P::NTHREADS + (TMA ? 32 : 0), 1, 1);
@@ -938,11 +947,15 @@ static int launch_pconv_step_tt(const PconvArgs &a, int channels, int S, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, pconv_step_kernel<LOGP, TV, TMA>, a));
+  CK(cudaLaunchKernelEx(&cfg, pconv_step_kernel<LOGP, TV, TMA, DEEP>, a));
   return B2F_OK;
 }
 template <int LOGP, bool TV>
-static int launch_pconv_step_t(const PconvArgs &a, int channels, int S, int tma_opt, cudaStream_t st) {
+static int launch_pconv_step_t(const PconvArgs &a, int channels, int S, int tma_opt, cudaStream_t st, bool deep = false) {
+  // At most one CTA per SM, partitions of 2048 / 4096 samples, long streams per CTA: the TMA feed with whole-frame stages (PconvGeom::deep_stages)
+  if constexpr (LOGP >= 11) {
+    if (deep && tma_opt != 0) return launch_pconv_step_tt<LOGP, TV, true, true>(a, channels, S, st);
+  }
   // Which MAC feeds the fused kernel: registers (128-bit loads, 16 in flight per thread) or the TMA ring. Measured on
   // B200 (480000 taps, fraction of the measured HBM peak, registers vs TMA; tools/pconv_sweep.py --feed-sweep,
   // profiles/r02_pconv_feed_sweep.txt): pts 512 1.10 vs 1.05; pts 1024 0.47 / 0.76 / 0.85 / 1.02 vs 0.40 / 0.66 /
@@ -992,13 +1005,14 @@ static int launch_pconv_push_t(const float *ir, size_t stride, b2f_pconv *h, cud
     default: return B2F_ERR_UNSUPPORTED; \
   }
 
-static int launch_pconv_step(int logp, bool tv, const PconvArgs &a, int channels, int S, int tma_opt, cudaStream_t st) {
+static int launch_pconv_step(int logp, bool tv, const PconvArgs &a, int channels, int S, int tma_opt, cudaStream_t st,
+                             bool deep = false) {
   if (tv) {
-#define CALL(L) launch_pconv_step_t<L, true>(a, channels, S, tma_opt, st)
+#define CALL(L) launch_pconv_step_t<L, true>(a, channels, S, tma_opt, st, deep)
     B2F_DISPATCH_LOGP(logp, CALL)
 #undef CALL
   } else {
-#define CALL(L) launch_pconv_step_t<L, false>(a, channels, S, tma_opt, st)
+#define CALL(L) launch_pconv_step_t<L, false>(a, channels, S, tma_opt, st, deep)
     B2F_DISPATCH_LOGP(logp, CALL)
 #undef CALL
   }
@@ -1053,6 +1067,10 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
     S = (int)f;
   }
   h->cluster = S;
+  // Measured (tools/pconv_few_channels_probe.py, profiles/r02_pconv_few_channels.txt): mono, pts 2048 x 2048 partitions
+  // 121 -> 55 us per block; no gain or a loss when a CTA streams only a few dozen partitions (16 channels x 234: 45.4 vs
+  // 46.5 us) and at pts 1024 (register feed: 19.6 vs 24.8 us)
+  h->deep = h->opt.pconv_deep_ring != 0 && logp >= 11 && (long long)channels * S <= sm_count() && h->nparts / S >= 96;
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "stream"));
   if (logp <= kPconvMaxLogP) {
@@ -1075,6 +1093,18 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
       return fail(cuda_fail(e, "cudaMalloc pad"));
     if ((e = cudaMalloc((void **)&h->d_Y, (size_t)channels * pts * sizeof(float2))) != cudaSuccess)
       return fail(cuda_fail(e, "cudaMalloc Y"));
+    {
+      // enough MAC CTAs for two per SM, every CTA keeping at least 8 partitions (measured, mono, pts 8192: 512
+      // partitions 170 -> see profiles/r02_rt_ratio_grid.txt)
+      const long long tiles = (long long)(pts / kMacTileBins) * channels;
+      long long K = h->opt.pconv_ksplit > 0 ? h->opt.pconv_ksplit : (2LL * sm_count() + tiles - 1) / tiles;
+      if (K > h->nparts / 8) K = h->nparts / 8;
+      if (K > 64) K = 64;
+      if (K < 1 || h->opt.pconv_ksplit < 0) K = 1;
+      h->ksplit = (int)K;
+      if (K > 1 && (e = cudaMalloc((void **)&h->d_Ypart, (size_t)K * channels * pts * sizeof(float2))) != cudaSuccess)
+        return fail(cuda_fail(e, "cudaMalloc Ypart"));
+    }
     if ((e = cudaMalloc((void **)&h->d_state, 2 * sizeof(int))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc state"));
     const int st0[2] = {h->wp, h->wp2};
     if ((e = cudaMemcpy(h->d_state, st0, sizeof(st0), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "state"));
@@ -1132,7 +1162,46 @@ static int pconv_general_frame(b2f_pconv *h, const float *x, size_t stride, floa
                        cudaMemcpyDeviceToDevice, st));
   return B2F_OK;
 }
+// pts = 8192 / 16384 with fewer channels than the one-SM FFT kernel wants: the general path's transforms run on the
+// register-level kernels fused with their neighbours (pconv_kernels.cuh: frames, inverse + overlap-add + advance, and
+// push_ir in one launch) -- 11-12 launches per time-varying block become 3-4
+static bool pconv_general_fused(const b2f_pconv *h) {
+  return h->opt.pconv_general_fused != 0 && (h->logp == 13 || h->logp == 14) && !h->gfwd->sm.use_for(h->channels);
+}
+template <int LOGP>
+static int pconv_general_push_fused_t(b2f_pconv *h, const float *ir, size_t stride, cudaStream_t st) {
+  using B = BatchGeom<LOGP>;
+  int rc = set_smem(pconv_push_ir_reg_kernel<LOGP>, B::SMEM_BYTES);
+  if (rc) return rc;
+  dim3 grid((h->nparts + B::TPB - 1) / B::TPB, h->channels, 1);
+  pconv_push_ir_reg_kernel<LOGP><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(ir, stride, h->d_irs, h->gfwd->d_tw, h->gfwd->d_hw, h->nparts, h->wp2);
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
+template <int LOGP>
+static int pconv_general_frames_fused_t(b2f_pconv *h, bool tv, const float *d_in1, const float *d_in2, cudaStream_t st) {
+  using B = BatchGeom<LOGP>;
+  int rc = set_smem(pconv_frames_reg_kernel<LOGP>, B::SMEM_BYTES);
+  if (rc) return rc;
+  dim3 grid(h->channels, tv ? 2 : 1, 1);
+  pconv_frames_reg_kernel<LOGP><<<grid, B::THREADS, B::SMEM_BYTES, st>>>(d_in1, d_in2, (size_t)h->pts, h->d_fdl, h->d_irs, h->gfwd->d_tw,
+                                                                       h->gfwd->d_hw, h->nparts, h->d_state);
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
+template <int LOGP>
+static int pconv_general_inverse_fused_t(b2f_pconv *h, bool tv, float *d_out, cudaStream_t st) {
+  using B = BatchGeom<LOGP>;
+  int rc = set_smem(pconv_inverse_ola_kernel<LOGP>, B::SMEM_BYTES);
+  if (rc) return rc;
+  pconv_inverse_ola_kernel<LOGP><<<h->channels, B::THREADS, B::SMEM_BYTES, st>>>(h->d_Y, h->d_tail, d_out, h->ginv->d_tw, h->ginv->d_hw,
+                                                                              h->d_state, h->nparts, tv ? 1 : 0);
+  CK(cudaGetLastError());
+  return B2F_OK;
+}
 static int pconv_general_push(b2f_pconv *h, const float *ir, size_t stride, cudaStream_t st) {
+  if (pconv_general_fused(h))
+    return h->logp == 13 ? pconv_general_push_fused_t<13>(h, ir, stride, st) : pconv_general_push_fused_t<14>(h, ir, stride, st);
   for (int i = 0; i < h->nparts; i++) {
     int frame = (h->wp2 - i) % h->nparts;
     if (frame < 0) frame += h->nparts;
@@ -1158,20 +1227,37 @@ static int pconv_general_frame_state(b2f_pconv *h, const float *x, float2 *ring,
 // them: the sequence is the same for every block, which is what lets the host call replay it as a CUDA graph.
 static int pconv_general_step(b2f_pconv *h, bool tv, float *d_out, const float *d_in1, const float *d_in2, cudaStream_t st) {
   const int pts = h->pts;
-  int rc = pconv_general_frame_state(h, d_in1, h->d_fdl, 0, st);
-  if (rc) return rc;
-  if (tv && (rc = pconv_general_frame_state(h, d_in2, h->d_irs, 1, st))) return rc;
+  const bool fused = pconv_general_fused(h);
+  int rc;
+  if (fused) {
+    rc = h->logp == 13 ? pconv_general_frames_fused_t<13>(h, tv, d_in1, d_in2, st) : pconv_general_frames_fused_t<14>(h, tv, d_in1, d_in2, st);
+    if (rc) return rc;
+  } else {
+    if ((rc = pconv_general_frame_state(h, d_in1, h->d_fdl, 0, st))) return rc;
+    if (tv && (rc = pconv_general_frame_state(h, d_in2, h->d_irs, 1, st))) return rc;
+  }
   // TMA-fed MAC by default on this path (measured 3-16 % faster with many channels, 2x for a mono 4M-tap IR);
   // option pconv_tma = 0 selects the register-fed kernel.
+  // Few channels: the partitions are split over grid.z (ksplit CTAs per tile, partial sums in d_Ypart, added in
+  // ascending order by a second launch), so that a mono stream with a long IR still covers the GPU
+  const int K = h->ksplit;
+  float2 *macY = K > 1 ? h->d_Ypart : h->d_Y;
   if (h->opt.pconv_tma != 0) {
     if ((rc = set_smem(pconv_mac_tma_kernel, kMacTmaSmem))) return rc;
-    dim3 gt(pts / kMacTileBins, h->channels, 1);
-    pconv_mac_tma_kernel<<<gt, 288, kMacTmaSmem, st>>>(h->d_fdl, h->d_irs, h->d_Y, pts, h->nparts, h->d_state);
+    dim3 gt(pts / kMacTileBins, h->channels, K);
+    pconv_mac_tma_kernel<<<gt, 288, kMacTmaSmem, st>>>(h->d_fdl, h->d_irs, macY, pts, h->nparts, h->d_state);
   } else {
-    dim3 gm((pts / 2 + 255) / 256, h->channels, 1);
-    pconv_mac_kernel<<<gm, 256, 0, st>>>(h->d_fdl, h->d_irs, h->d_Y, pts, h->nparts, h->d_state);
+    dim3 gm((pts / 2 + 255) / 256, h->channels, K);
+    pconv_mac_kernel<<<gm, 256, 0, st>>>(h->d_fdl, h->d_irs, macY, pts, h->nparts, h->d_state);
   }
   CK(cudaGetLastError());
+  if (K > 1) {
+    const size_t total4 = (size_t)h->channels * pts / 2;
+    pconv_mac_sum_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>((const float4 *)h->d_Ypart, (float4 *)h->d_Y, total4, K);
+    CK(cudaGetLastError());
+  }
+  if (fused)
+    return h->logp == 13 ? pconv_general_inverse_fused_t<13>(h, tv, d_out, st) : pconv_general_inverse_fused_t<14>(h, tv, d_out, st);
   if ((rc = h->ginv->run_real(h->d_Y, h->d_Y, h->channels, st))) return rc;
   dim3 go((pts + 255) / 256, h->channels, 1);
   pconv_ola_kernel<<<go, 256, 0, st>>>((const float *)h->d_Y, h->d_tail, d_out, pts);
@@ -1214,7 +1300,7 @@ static int pconv_enqueue(b2f_pconv *h, bool tv, float *d_out, const float *d_in1
   a.tw = h->d_tw, a.w2 = h->d_w2;
   a.nparts = h->nparts, a.wp = h->wp, a.wp2 = h->wp2;
   int rc = h->general() ? pconv_general_step(h, tv, d_out, d_in1, d_in2, st)
-                        : launch_pconv_step(h->logp, tv, a, h->channels, h->cluster, (int)h->opt.pconv_tma, st);
+                        : launch_pconv_step(h->logp, tv, a, h->channels, h->cluster, (int)h->opt.pconv_tma, st, h->deep);
   if (rc) return rc;
   h->wp = h->wp != h->nparts - 1 ? h->wp + 1 : 0;             // cl_conv.cpp:424
   if (tv) h->wp2 = h->wp2 == 0 ? h->nparts - 1 : h->wp2 - 1;  // cl_conv.cpp:519
@@ -1255,6 +1341,7 @@ static int pconv_host_bufs(b2f_pconv *h, bool tv) {
 // from the very code the device entry points run (pconv_general_step) on the handle's fixed buffers. The ring
 // positions are device-resident, so no node parameter changes between blocks. Blocks above the bounce limit (the
 // throughput regime) and option graph = 0 take the plain stream path.
+static const size_t kGraphZeroCopyMax = 128u << 10;
 static int pconv_graph_call(b2f_pconv *h, bool tv, float *out, const float *in1, const float *in2) {
   const size_t blk = (size_t)h->channels * h->pts * sizeof(float);
   int rc;
@@ -1264,11 +1351,18 @@ static int pconv_graph_call(b2f_pconv *h, bool tv, float *out, const float *in1,
   if (!ge) {
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
-    cudaError_t e = cudaMemcpyAsync(h->d_in1, h->sg_in.pin, blk, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess && tv) e = cudaMemcpyAsync(h->d_in2, h->sg_in2.pin, blk, cudaMemcpyHostToDevice, h->stream);
-    rc = e == cudaSuccess ? pconv_general_step(h, tv, h->d_out, h->d_in1, h->d_in2, h->stream) : cuda_fail(e, "capture H2D");
-    if (!rc && (e = cudaMemcpyAsync(h->sg_out.pin, h->d_out, blk, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
-      rc = cuda_fail(e, "capture D2H");
+    cudaError_t e = cudaSuccess;
+    if (blk <= kGraphZeroCopyMax) {
+      // a few channels: the block's first kernel reads the pinned staging buffers and its last one writes the pinned
+      // result directly (three copy nodes fewer: a mono 8192-sample block is 32 KB each way)
+      rc = pconv_general_step(h, tv, (float *)h->sg_out.pin, (const float *)h->sg_in.pin, (const float *)h->sg_in2.pin, h->stream);
+    } else {
+      e = cudaMemcpyAsync(h->d_in1, h->sg_in.pin, blk, cudaMemcpyHostToDevice, h->stream);
+      if (e == cudaSuccess && tv) e = cudaMemcpyAsync(h->d_in2, h->sg_in2.pin, blk, cudaMemcpyHostToDevice, h->stream);
+      rc = e == cudaSuccess ? pconv_general_step(h, tv, h->d_out, h->d_in1, h->d_in2, h->stream) : cuda_fail(e, "capture H2D");
+      if (!rc && (e = cudaMemcpyAsync(h->sg_out.pin, h->d_out, blk, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+        rc = cuda_fail(e, "capture D2H");
+    }
     e = cudaStreamEndCapture(h->stream, &g);
     if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamEndCapture");
     if (!rc && (e = cudaGraphInstantiate(&ge, g, 0)) != cudaSuccess) rc = cuda_fail(e, "cudaGraphInstantiate");

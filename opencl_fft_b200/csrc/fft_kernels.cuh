@@ -171,24 +171,18 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
 }
 
 // inverse: in [batch][N] float2, out [batch][2N] float (may alias). hw: folded inverse table.
-template <int LOGN>
-__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
-    rfft_inv_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
-                        int batch, int ahead) {
+// OLA (Clpconv's last step, cl_conv_kernels.h:120-124): the transform's 2N reals are not stored; the last pass leaves
+// them in shared memory and the CTA writes out = (y[0, N) + tail) * ola_scale, tail = y[N, 2N).
+template <int LOGN, bool OLA>
+__device__ __forceinline__ void rfft_inv_reg_body(const float2 *src, float2 *dst, bool active, float2 *sm,
+                                                  const float2 *__restrict__ tw, const float2 *__restrict__ hw, int t,
+                                                  float2 *tail2 = nullptr, float ola_scale = 1.f) {
   using B = BatchGeom<LOGN>;
   using RS = RegSplitGeom<LOGN>;
   constexpr int N = 1 << LOGN, T = B::T, R0 = RS::R0, E = FftGeom<LOGN>::E, H = E / 2;
-  extern __shared__ float2 smem[];
-  const int lt = threadIdx.x / T, t = threadIdx.x % T;
-  const long long b = (long long)blockIdx.x * B::TPB + lt;
-  const bool active = b < batch;
-  const float2 *src = in + (active ? b : 0) * N;
-  float2 *dst = out + (active ? b : 0) * N;
-  float2 *sm = smem + lt * BatchGeom<LOGN>::ROW;
   // a thread reads its 8 low members X[t + m*T] and, straight from global memory, their partners X[N - (t + m*T)]
   // (the values its partner thread will own): 16 loads as before, and no exchange before the unsplit
   float2 x[E], hi[H];  // hi: unsplit high members, owned by the partner thread
-  prefetch_successor<LOGN>(in, ahead, batch);
   const int pt = (t == 0) ? 0 : T - t;
   const float2 zero2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -218,10 +212,37 @@ __global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN
   __syncthreads();  // staging is the engine's work buffer from here on
   // first pass: value index m of (idx, slot): idx = (t + q*T) + r*(N/R0), slot = q*R0 + r  ->  m = q + r*(E/R0)
   auto load = [&](int, int slot) { return x[(slot / R0) + (slot % R0) * (E / R0)]; };
-  auto store = [&](int idx, float2 v, int) {
-    if (active) __stcs(dst + idx, v);
-  };
-  fft_run<LOGN, true>(load, store, sm, tw, t, CtaSync());
+  if constexpr (!OLA) {
+    auto store = [&](int idx, float2 v, int) {
+      if (active) __stcs(dst + idx, v);
+    };
+    fft_run<LOGN, true>(load, store, sm, tw, t, CtaSync());
+  } else {
+    static_assert(B::TPB == 1, "the overlap-add epilogue assumes one transform per CTA");
+    auto store = [&](int idx, float2 v, int) { sm[pad_idx(idx)] = v; };
+    fft_run<LOGN, true, true>(load, store, sm, tw, t, CtaSync());
+    __syncthreads();
+    // element m holds the reals (y[2m], y[2m+1]); the thread that reads a tail element is the one that replaces it
+    for (int m = t; m < N / 2; m += T) {
+      const float2 y = sm[pad_idx(m)], z = sm[pad_idx(m + N / 2)], tl = tail2[m];
+      dst[m] = make_float2((y.x + tl.x) * ola_scale, (y.y + tl.y) * ola_scale);
+      tail2[m] = z;
+    }
+  }
+}
+template <int LOGN>
+__global__ void __launch_bounds__(BatchGeom<LOGN>::THREADS, BatchGeom<LOGN>::MIN_BLOCKS)
+    rfft_inv_reg_kernel(const float2 *in, float2 *out, const float2 *__restrict__ tw, const float2 *__restrict__ hw,
+                        int batch, int ahead) {
+  using B = BatchGeom<LOGN>;
+  constexpr int N = 1 << LOGN, T = B::T;
+  extern __shared__ float2 smem[];
+  const int lt = threadIdx.x / T, t = threadIdx.x % T;
+  const long long b = (long long)blockIdx.x * B::TPB + lt;
+  const bool active = b < batch;
+  prefetch_successor<LOGN>(in, ahead, batch);
+  rfft_inv_reg_body<LOGN, false>(in + (active ? b : 0) * N, out + (active ? b : 0) * N, active,
+                                 smem + lt * BatchGeom<LOGN>::ROW, tw, hw, t);
 }
 
 // =====================================================================================================

@@ -51,9 +51,21 @@ struct PconvGeom {
 #ifndef B2F_PCONV_STAGES12
 #define B2F_PCONV_STAGES12 5  // (build-time knob kept for re-measurement)
 #endif
-  __host__ __device__ static constexpr int stages(bool) { return LOGP >= 12 ? B2F_PCONV_STAGES12 : 6; }
   static constexpr int SLICE = HALF < NTHREADS ? HALF : NTHREADS;  // float4 per slice (16 B .. 4 KB)
-  __host__ __device__ static constexpr int ring_f4(bool tv) { return 2 * stages(tv) * SLICE; }
+  // DEEP ring, for launches with at most one CTA per SM (a few channels: the mono streams of csound/tests.py). A lone
+  // CTA is paced by its per-stage hand-shake (wait, two 128-bit reads, one multiply-add, arrive: ~470 cycles per 8 KB
+  // measured, 34-43 GB/s per CTA), not by the bytes in flight -- a 24-stage ring of the same 4 KB slices was SLOWER
+  // (mono pts 2048 x 2048 partitions 121 -> 125 us, pts 512 x 8192 66 -> 127 us). So a deep stage holds DEEP_TILES
+  // tiles of a partition (16 KB of FDL + 16 KB of IR): one hand-shake per 32 KB, and the ring takes the shared memory
+  // that the FFT buffers and the cluster partials leave.
+  static constexpr int DEEP_TILES = TILES > 4 ? 4 : TILES;
+  __host__ __device__ static constexpr int deep_stages() {
+    const int fixed = 2 * (FFT_SMEM + 1) * 8 + HALF * 16;  // both FFT buffers (time-varying) + cluster partials
+    const int n = (224 * 1024 - fixed) / (2 * DEEP_TILES * SLICE * 16 + 16);
+    return n > 12 ? 12 : (n < 2 ? 2 : n);
+  }
+  __host__ __device__ static constexpr int stages(bool deep) { return deep ? deep_stages() : (LOGP >= 12 ? B2F_PCONV_STAGES12 : 6); }
+  __host__ __device__ static constexpr int ring_f4(bool deep) { return 2 * stages(deep) * SLICE * (deep ? DEEP_TILES : 1); }
   // frames wider than the CTA whose tiles are swept together, one accumulator per tile (see pconv_step_kernel)
   __host__ __device__ static constexpr bool pmajor(bool tma) { return TILES > 1 && (tma || TILES == 2 || TILES == 4); }
   // float4 entries between the FFT buffers and the TMA ring: the cluster-partials buffer (clusters only), then the
@@ -202,8 +214,9 @@ struct PconvArgs {
 // from its shared memory instead.
 // TMA: the partitions are streamed by the TMA engine (cp.async.bulk, one producer warp, an mbarrier ring in
 // shared memory) instead of 128-bit loads into registers; block = NTHREADS + 32.
-template <int LOGP, bool TV, bool TMA>
+template <int LOGP, bool TV, bool TMA, bool DEEP = false>
 __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pconv_step_kernel(PconvArgs a) {
+  static_assert(TMA || !DEEP, "the deep ring is the TMA feed's");
   using P = PconvGeom<LOGP>;
   constexpr int PTS = P::PTS, HALF = P::HALF, NT = P::NTHREADS;
   extern __shared__ float4 smem4[];
@@ -214,7 +227,7 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
   const int rank = (int)cluster.block_rank();
   float4 *sP = reinterpret_cast<float4 *>(sG + (TV ? P::FFT_SMEM + (P::FFT_SMEM & 1) : 0));  // cluster partials [HALF], S > 1
   float4 *sPark = sP + (S > 1 ? HALF : 0);                // Y of the tile-by-tile sweep [HALF]
-  constexpr int STAGES = P::stages(TV), RING_F4 = P::ring_f4(TV);
+  constexpr int STAGES = P::stages(DEEP), RING_F4 = P::ring_f4(DEEP);
   constexpr bool PMAJOR = P::pmajor(TMA);
   float4 *ring = sP + P::partial_f4(TMA, S);              // TMA ring: [STAGES][2][SLICE] float4, then barriers
   const bool worker = !TMA || threadIdx.x < NT;           // false only for the producer warp
@@ -295,6 +308,42 @@ __global__ void __launch_bounds__(PconvGeom<LOGP>::NTHREADS + (TMA ? 32 : 0)) pc
       const unsigned char *Fb = reinterpret_cast<const unsigned char *>(fdl);
       const unsigned char *Gb = reinterpret_cast<const unsigned char *>(irs);
       const size_t frame_bytes = (size_t)PTS * sizeof(float2);
+      if constexpr (DEEP) {
+        // one stage = DT tiles of a partition: a single hand-shake per 2 x DT x 4 KB
+        constexpr int DT = P::DEEP_TILES, GROUPS = TL / DT;
+        constexpr uint32_t kStageBytes = DT * kSliceBytes;
+        for (int p = p_lo; p < p_hi; p++) {
+          if (p == p_newx || p == p_newg) continue;
+          const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
+#pragma unroll
+          for (int g = 0; g < GROUPS; g++) {
+            const uint32_t s = slot % STAGES, round = slot / STAGES;
+            float4 *stF = ring + (size_t)(2 * s) * DT * P::SLICE, *stG = stF + DT * P::SLICE;
+            if (!worker) {
+              if ((tid & 31) == 0) {
+                if (round > 0) tma::mbar_wait(bar_empty + 8 * s, (round - 1) & 1);
+                tma::mbar_expect_tx(bar_full + 8 * s, 2 * kStageBytes);
+                tma::bulk_g2s(tma::smem_u32(stF), Fb + (size_t)frame * frame_bytes + g * kStageBytes, kStageBytes, bar_full + 8 * s);
+                tma::bulk_g2s(tma::smem_u32(stG), Gb + (size_t)p * frame_bytes + g * kStageBytes, kStageBytes, bar_full + 8 * s);
+              }
+            } else {
+              tma::mbar_wait(bar_full + 8 * s, round & 1);
+#pragma unroll
+              for (int u = 0; u < DT; u++) {
+                const float4 fa = stF[u * P::SLICE + tid], gb = stG[u * P::SLICE + tid];
+                cmac2(acc[g * DT + u], fa, gb);
+                if (g == 0 && u == 0) {
+                  acc0.x += fa.x * gb.x;
+                  acc0.y += fa.y * gb.y;
+                }
+              }
+              __syncwarp();
+              if ((tid & 31) == 0) tma::mbar_arrive(bar_empty + 8 * s);
+            }
+            slot++;
+          }
+        }
+      } else
       for (int p = p_lo; p < p_hi; p++) {
         if (p == p_newx || p == p_newg) continue;
         const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
@@ -660,6 +709,41 @@ __global__ void __launch_bounds__(BatchGeom<LOGP>::THREADS, BatchGeom<LOGP>::MIN
                                 (reinterpret_cast<uintptr_t>(x) & 7) == 0, smem_push + lt * B::ROW, tw, hw, t, 1.0f);
 }
 
+// General path, pts = 8192 / 16384 (below): the block's new frames -- R(in1) into FDL frame state[0] and, time-varying,
+// R(in2) into IR frame state[1] -- in ONE launch on the same register-level transform (instead of pad, batched rFFT
+// and frame copy, three launches per input). grid = (channels, 1 or 2).
+template <int LOGP>
+__global__ void __launch_bounds__(BatchGeom<LOGP>::THREADS, BatchGeom<LOGP>::MIN_BLOCKS)
+    pconv_frames_reg_kernel(const float *in1, const float *in2, size_t in_stride, float2 *fdl, float2 *irs,
+                            const float2 *__restrict__ tw, const float2 *__restrict__ hw, int nparts, const int *state) {
+  static_assert(BatchGeom<LOGP>::TPB == 1, "one frame per CTA");
+  constexpr int PTS = 1 << LOGP;
+  extern __shared__ float2 smem_push[];
+  const int ch = blockIdx.x, which = blockIdx.y;
+  const float *x = (which ? in2 : in1) + (size_t)ch * in_stride;
+  float2 *ring = which ? irs : fdl;
+  rfft_fwd_reg_body<LOGP, true>(reinterpret_cast<const float2 *>(x), ring + ((size_t)ch * nparts + state[which]) * PTS, true,
+                                (reinterpret_cast<uintptr_t>(x) & 7) == 0, smem_push, tw, hw, threadIdx.x, 1.0f);
+}
+// ... and the block's last three launches in one: inverse real transform of Y, overlap-add with the saved tail
+// (cl_conv_kernels.h:120-124), ring positions advanced (cl_conv.cpp:424, 519). grid = channels.
+template <int LOGP>
+__global__ void __launch_bounds__(BatchGeom<LOGP>::THREADS, BatchGeom<LOGP>::MIN_BLOCKS)
+    pconv_inverse_ola_kernel(const float2 *Y, float *tail, float *out, const float2 *__restrict__ tw,
+                             const float2 *__restrict__ hw, int *state, int nparts, int tv) {
+  static_assert(BatchGeom<LOGP>::TPB == 1, "one transform per CTA");
+  constexpr int PTS = 1 << LOGP;
+  extern __shared__ float2 smem_push[];
+  const int ch = blockIdx.x;
+  rfft_inv_reg_body<LOGP, true>(Y + (size_t)ch * PTS, reinterpret_cast<float2 *>(out + (size_t)ch * PTS), true, smem_push, tw,
+                                hw, threadIdx.x, reinterpret_cast<float2 *>(tail + (size_t)ch * PTS), 1.0f / (float)PTS);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // nobody in this launch reads the positions
+    const int wp = state[0], wp2 = state[1];
+    state[0] = wp + 1 == nparts ? 0 : wp + 1;
+    if (tv) state[1] = wp2 == 0 ? nparts - 1 : wp2 - 1;
+  }
+}
+
 // =====================================================================================================
 // General path for partitions too long for the fused kernel (pts = 8192 .. 32768, the upper half of the
 // partition sizes swept by the reference's csound/tests.py:10). The FFTs run on the batched real-FFT
@@ -714,14 +798,30 @@ __global__ void __launch_bounds__(256)
   const float4 *G = reinterpret_cast<const float4 *>(irs) + chan4 + q;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float2 acc0 = make_float2(0.f, 0.f);
+  // this CTA's share of the partitions (grid.z splits them when there are too few CTAs otherwise; see pconv_mac_sum_kernel)
+  const int p0 = (int)((long long)blockIdx.z * nparts / gridDim.z), p1 = (int)((long long)(blockIdx.z + 1) * nparts / gridDim.z);
   const int wrap = nparts - rp;  // partitions [0, wrap) read frames rp.., [wrap, nparts) read frames 0..
-  mac_segment<8>(acc, acc0, F + (size_t)rp * stride4, G, wrap, stride4);
-  mac_segment<8>(acc, acc0, F, G + (size_t)wrap * stride4, nparts - wrap, stride4);
+  const int m = wrap < p0 ? p0 : (wrap > p1 ? p1 : wrap);
+  mac_segment<8>(acc, acc0, F + (size_t)(rp + p0) * stride4, G + (size_t)p0 * stride4, m - p0, stride4);
+  mac_segment<8>(acc, acc0, F + (size_t)(m - wrap) * stride4, G + (size_t)m * stride4, p1 - m, stride4);
   if (q == 0) {
     acc.x = acc0.x;
     acc.y = acc0.y;
   }
-  reinterpret_cast<float4 *>(Y)[(size_t)ch * stride4 + q] = acc;
+  reinterpret_cast<float4 *>(Y)[((size_t)blockIdx.z * gridDim.y + ch) * stride4 + q] = acc;
+}
+// Y[ch][n] = sum_k part[k][ch][n], ascending k: the second half of a MAC whose partitions were split over grid.z
+// (few channels, long IR: pts / 512 x channels CTAs streaming all partitions one after the other leave most of the GPU
+// idle -- mono, pts 8192 x 512 partitions: 16 CTAs). total4 = channels * pts / 2 float4 per part.
+__global__ void pconv_mac_sum_kernel(const float4 *part, float4 *Y, size_t total4, int K) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  float4 a = part[i];
+  for (int k = 1; k < K; k++) {
+    const float4 b = part[(size_t)k * total4 + i];
+    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+  }
+  Y[i] = a;
 }
 
 // ---- the same MAC fed by the TMA engine -----------------------------------------------------------------------
@@ -760,10 +860,12 @@ __global__ void __launch_bounds__(288)
     tma::fence_barrier_init();
   }
   __syncthreads();
+  // this CTA's share of the partitions (grid.z; see pconv_mac_sum_kernel)
+  const int p0 = (int)((long long)blockIdx.z * nparts / gridDim.z), p1 = (int)((long long)(blockIdx.z + 1) * nparts / gridDim.z);
   if (warp == 8) {
     if ((tid & 31) == 0) {
-      for (int p = 0; p < nparts; p++) {
-        const int s = p % kMacStages, round = p / kMacStages;
+      for (int p = p0; p < p1; p++) {
+        const int s = (p - p0) % kMacStages, round = (p - p0) / kMacStages;
         if (round > 0) tma::mbar_wait(empty0 + 8 * s, (round - 1) & 1);  // consumers released the stage
         const int frame = (rp + p < nparts) ? rp + p : rp + p - nparts;
         tma::mbar_expect_tx(full0 + 8 * s, 2 * kMacSliceBytes);
@@ -775,8 +877,8 @@ __global__ void __launch_bounds__(288)
   }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float2 acc0 = make_float2(0.f, 0.f);
-  for (int p = 0; p < nparts; p++) {
-    const int s = p % kMacStages, round = p / kMacStages;
+  for (int p = p0; p < p1; p++) {
+    const int s = (p - p0) % kMacStages, round = (p - p0) / kMacStages;
     tma::mbar_wait(full0 + 8 * s, round & 1);
     const float4 a = ringF[s * (kMacSliceBytes / 16) + tid], b = ringG[s * (kMacSliceBytes / 16) + tid];
     cmac2(acc, a, b);
@@ -789,7 +891,7 @@ __global__ void __launch_bounds__(288)
     acc.x = acc0.x;
     acc.y = acc0.y;
   }
-  reinterpret_cast<float4 *>(Y)[(size_t)ch * (pts / 2) + (size_t)tile * 256 + tid] = acc;
+  reinterpret_cast<float4 *>(Y)[((size_t)blockIdx.z * gridDim.y + ch) * (pts / 2) + (size_t)tile * 256 + tid] = acc;
 }
 
 // y [channels][2*pts] (inverse transform, unnormalised) -> out = (y[0,pts) + tail) / pts, tail = y[pts, 2pts)

@@ -384,6 +384,33 @@ def test_ring_wrap_for_every_cluster_size(eng, port, options, cluster):
         assert rel_l2(ytv[:, k], np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])) < TOL
 
 
+@pytest.mark.parametrize("pts", [2048, 4096])
+def test_deep_ring_for_long_streams(eng, port, options, pts):
+    """Few channels, long IR: CTAs that stream >= 96 partitions each take the TMA feed with 32 KB stages (option
+    pconv_deep_ring). Same partition order per bin, so the same bits as the 4 KB-slice feed; and the oracle's values,
+    static and time-varying, over a full wrap of the delay line."""
+    nparts, channels = 200, 2
+    cvs, nb = nparts * pts, nparts + 3
+    rng = np.random.default_rng(pts + 1)
+    ir = (rng.standard_normal((channels, cvs)) * 0.02).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, channels, pts)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, channels, pts)) * 0.02).astype(np.float32)
+    options("pconv_cluster", 2)
+    res = {}
+    for deep in (1, 0):
+        options("pconv_deep_ring", deep)
+        c = eng.Clpconv(0, cvs, pts, channels=channels)
+        assert c.get_cl_err() == 0 and c.push_ir(ir) == 0
+        ctv = eng.Clpconv(0, cvs, pts, channels=channels)
+        res[deep] = (run_stream(c, x), run_stream(ctv, x, x2))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    o = port.pconv(cvs, pts)
+    o.push_ir(ir[1])
+    assert rel_l2(res[1][0][:, 1], np.stack([o.convolution(x[t, 1]) for t in range(nb)])) < TOL
+    o = port.pconv(cvs, pts)
+    assert rel_l2(res[1][1][:, 1], np.stack([o.convolution(x[t, 1], x2[t, 1]) for t in range(nb)])) < TOL
+
+
 def test_invalid_cluster_option_is_rejected_at_create(eng, options):
     options("pconv_cluster", 3)
     assert eng.Clpconv(0, 4096, 512, uData=1).get_cl_err() == 2
@@ -419,6 +446,60 @@ def test_graph_replay_equals_stream_launches(eng, port, options, pts, channels):
     assert rel_l2(res[1][0][:, 0], np.stack([o.convolution(x[t, 0]) for t in range(nb)])) < TOL
     o = port.pconv(cvs, pts)
     assert rel_l2(res[1][1][:, 0], np.stack([o.convolution(x[t, 0], x2[t, 0]) for t in range(nb)])) < TOL
+
+
+@pytest.mark.parametrize("ksplit", [0, 3, -1])
+def test_general_path_partition_split(eng, port, options, ksplit):
+    """pts >= 8192 with few channels: the partitions of the multiply-accumulate are split over several CTAs per tile
+    and the partial sums added by a second launch (option pconv_ksplit; 0 = measured choice, here 5). The oracle's
+    values, static and time-varying, over more than a full wrap of the delay line."""
+    options("pconv_ksplit", ksplit)
+    pts, nparts, channels = 8192, 40, 1
+    cvs, nb = nparts * pts, nparts + 3
+    rng = np.random.default_rng(7)
+    ir = (rng.standard_normal((channels, cvs)) * 0.02).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, channels, pts)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, channels, pts)) * 0.02).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts, channels=channels)
+    assert c.get_cl_err() == 0 and c.push_ir(ir) == 0
+    y = run_stream(c, x)
+    ctv = eng.Clpconv(0, cvs, pts, channels=channels)
+    ytv = run_stream(ctv, x, x2)
+    o = port.pconv(cvs, pts)
+    o.push_ir(ir[0])
+    assert rel_l2(y[:, 0], np.stack([o.convolution(x[t, 0]) for t in range(nb)])) < TOL
+    o = port.pconv(cvs, pts)
+    assert rel_l2(ytv[:, 0], np.stack([o.convolution(x[t, 0], x2[t, 0]) for t in range(nb)])) < TOL
+
+
+@pytest.mark.parametrize("pts,channels", [(8192, 3), (16384, 2)])
+def test_general_path_fused_launches_same_bits(eng, port, options, pts, channels):
+    """pts 8192 / 16384: the block's frames (pad + rFFT + frame copy, per input) and its tail (inverse rFFT + overlap-add
+    + ring advance) run as one launch each on the register-level transforms, and push_ir as one launch for all
+    partitions. Same arithmetic as the separate launches (option pconv_general_fused = 0): same bits; and the oracle's
+    values."""
+    nparts = 5
+    cvs, nb = nparts * pts, 2 * nparts + 2
+    rng = np.random.default_rng(pts + channels)
+    ir = (rng.standard_normal((channels, cvs)) * 0.05).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, channels, pts)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, channels, pts)) * 0.05).astype(np.float32)
+    res = {}
+    for fused in (1, 0):
+        options("pconv_general_fused", fused)
+        c = eng.Clpconv(0, cvs, pts, channels=channels)
+        assert c.get_cl_err() == 0 and c.push_ir(ir) == 0
+        spec = c.read_spectra(2, channels - 1)
+        ctv = eng.Clpconv(0, cvs, pts, channels=channels)
+        res[fused] = (run_stream(c, x), run_stream(ctv, x, x2), spec)
+    assert np.array_equal(res[0][2], res[1][2])
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    k = channels - 1
+    o = port.pconv(cvs, pts)
+    o.push_ir(ir[k])
+    assert rel_l2(res[1][0][:, k], np.stack([o.convolution(x[t, k]) for t in range(nb)])) < TOL
+    o = port.pconv(cvs, pts)
+    assert rel_l2(res[1][1][:, k], np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])) < TOL
 
 
 def test_python_binding_rejects_short_buffers(eng):
