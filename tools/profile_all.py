@@ -1,5 +1,5 @@
 """Launch ONE hot kernel family a couple of times at its BASELINE shape, for `ncu --set full`:
-    python tools/profile_all.py cfft1024 | rfft4096 | rfft65536 | pconv5b | pconv_general | dconv4
+    python tools/profile_all.py cfft1024 | rfft4096 | rfft65536 | pconv5b | pconv_general | dconv4 | push_ir | pconv_mono_deep | pconv_general_mono
 (see profiles/r01_ncu_all_kernels.md for the command line used)."""
 import os
 import sys
@@ -46,6 +46,23 @@ elif wl == "pconv_general":  # 64 channels x 2^20-tap IR, 8192-sample partitions
     yg = torch.empty_like(xg)
     for _ in range(reps):
         cg.convolution_dev(yg, xg)
+elif wl == "push_ir":  # config 5b's set-up, 256-channel slice
+    conv = eng.Clpconv(0, 480000, 512, channels=256)
+    ir = torch.randn(256, 480000, device="cuda") * 0.01
+    for _ in range(reps):
+        conv.push_ir_dev(ir, 480000)
+elif wl == "pconv_mono_deep":  # one channel, 4M-tap IR, 2048-sample partitions: cluster of 16, 32 KB TMA stages
+    cm = eng.Clpconv(0, 1 << 22, 2048, channels=1)
+    xm = torch.rand(1, 2048, device="cuda")
+    ym = torch.empty_like(xm)
+    for _ in range(reps + 2):
+        cm.convolution_dev(ym, xm, xm)
+elif wl == "pconv_general_mono":  # one channel, 4M-tap IR, 8192-sample partitions: fused frames / split MAC / inverse + OLA
+    cm = eng.Clpconv(0, 1 << 22, 8192, channels=1)
+    xm = torch.rand(1, 8192, device="cuda")
+    ym = torch.empty_like(xm)
+    for _ in range(reps + 2):
+        cm.convolution_dev(ym, xm, xm)
 elif wl == "dconv4":
     d = eng.Cldconv(0, 4096, 256, channels=64)
     d.push_ir_dev(torch.randn(64, 4096, device="cuda") / 64, 4096)
