@@ -106,7 +106,10 @@ int b2f_cfft_create(b2f_cfft **plan, int device, int N, int fwd, int max_batch);
 int b2f_cfft_destroy(b2f_cfft *plan);
 /* Clcfft::transform (cl_fft.cpp:153-161): in place on `batch` consecutive N-point host arrays */
 int b2f_cfft_exec_host(b2f_cfft *plan, float *c, int batch);
-/* device-resident: in/out [batch][N] complex, may alias; asynchronous on `stream` */
+/* device-resident: in/out [batch][N] complex, may alias; asynchronous on `stream`. Stream order is kept as for any
+ * kernel launch. (The 16384 / 32768-point kernels are launched with programmatic stream serialisation: a following
+ * launch of theirs may be SCHEDULED while the previous one drains, but reads and writes nothing before the previous
+ * kernel has completed and flushed -- griddepcontrol.wait -- so dependent calls on one stream need no extra care.) */
 int b2f_cfft_exec_dev(b2f_cfft *plan, const void *d_in, void *d_out, int batch, void *stream);
 
 /* ---- real FFT: cl_fft::Clrfft (cl_fft.h:74-111, cl_fft.cpp:208-296) -----------------------
