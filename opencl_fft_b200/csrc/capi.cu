@@ -966,6 +966,42 @@ static int launch_pconv_step_t(const PconvArgs &a, int channels, int S, int tma_
   return use_tma ? launch_pconv_step_tt<LOGP, TV, true>(a, channels, S, st)
                  : launch_pconv_step_tt<LOGP, TV, false>(a, channels, S, st);
 }
+// Can the device co-schedule a cluster of S CTAs of the step kernel this handle would launch? (Clusters of 16 need
+// 16 free SMs of ONE GPC at up to 198 KB of shared memory each: true on a full B200, not guaranteed on every part.)
+template <int LOGP, bool TV, bool TMA, bool DEEP>
+static bool pconv_cluster_fits_tt(int S) {
+  using P = PconvGeom<LOGP>;
+  auto kern = pconv_step_kernel<LOGP, TV, TMA, DEEP>;
+  const int smem = pconv_smem_bytes<LOGP>(TV, TMA, S, DEEP);
+  if (set_smem(kern, smem)) return false;
+  if (S > 8 && allow_cluster16_once((const void *)kern)) return false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(S, 1, 1);
+  cfg.blockDim = dim3(P::NTHREADS + (TMA ? 32 : 0), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return n >= 1;
+}
+template <int LOGP>
+static int pconv_cluster_fits_t(int S, int tma_opt, bool deep) {  // both block kinds (static and time-varying)
+  if constexpr (LOGP >= 11) {
+    if (deep && tma_opt != 0) return pconv_cluster_fits_tt<LOGP, false, true, true>(S) && pconv_cluster_fits_tt<LOGP, true, true, true>(S);
+  }
+  const bool use_tma = tma_opt >= 0 ? tma_opt == 1 : LOGP >= 11;
+  return use_tma ? pconv_cluster_fits_tt<LOGP, false, true, false>(S) && pconv_cluster_fits_tt<LOGP, true, true, false>(S)
+                 : pconv_cluster_fits_tt<LOGP, false, false, false>(S) && pconv_cluster_fits_tt<LOGP, true, false, false>(S);
+}
 template <int LOGP>
 static int launch_pconv_push_t(const float *ir, size_t stride, b2f_pconv *h, cudaStream_t st) {
   if constexpr (RegSplitGeom<LOGP>::OK) {
@@ -1016,6 +1052,11 @@ static int launch_pconv_step(int logp, bool tv, const PconvArgs &a, int channels
     B2F_DISPATCH_LOGP(logp, CALL)
 #undef CALL
   }
+}
+static int pconv_cluster_fits(int logp, int S, int tma_opt, bool deep) {
+#define CALL(L) pconv_cluster_fits_t<L>(S, tma_opt, deep)
+  B2F_DISPATCH_LOGP(logp, CALL)
+#undef CALL
 }
 static int launch_pconv_push(int logp, const float *ir, size_t stride, b2f_pconv *h, cudaStream_t st) {
 #define CALL(L) launch_pconv_push_t<L>(ir, stride, h, st)
@@ -1071,6 +1112,11 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   // 121 -> 55 us per block; no gain or a loss when a CTA streams only a few dozen partitions (16 channels x 234: 45.4 vs
   // 46.5 us) and at pts 1024 (register feed: 19.6 vs 24.8 us)
   h->deep = h->opt.pconv_deep_ring != 0 && logp >= 11 && (long long)channels * S <= sm_count() && h->nparts / S >= 96;
+  if (S == 16 && !h->opt.pconv_cluster && logp <= kPconvMaxLogP && pconv_cluster_fits(logp, 16, (int)h->opt.pconv_tma, h->deep) != 1) {
+    // this device cannot co-schedule 16 such CTAs: the portable limit it is
+    S = h->cluster = 8;
+    h->deep = h->opt.pconv_deep_ring != 0 && logp >= 11 && (long long)channels * S <= sm_count() && h->nparts / S >= 96;
+  }
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "stream"));
   if (logp <= kPconvMaxLogP) {

@@ -411,6 +411,29 @@ def test_deep_ring_for_long_streams(eng, port, options, pts):
     assert rel_l2(res[1][1][:, 1], np.stack([o.convolution(x[t, 1], x2[t, 1]) for t in range(nb)])) < TOL
 
 
+@pytest.mark.parametrize("nparts", [128, 1600])
+def test_mono_long_ir_4096_sample_partitions(eng, port, nparts):
+    """One channel, 4096-sample partitions, long IR: the measured choice is a cluster of 16 CTAs (non-portable size; the
+    portable 8 where the device cannot co-schedule 16) and, from 96 partitions per CTA, 32 KB TMA stages at 198 KB of
+    shared memory per CTA. The oracle's values, static and time-varying."""
+    pts = 4096
+    cvs, nb = nparts * pts, 5
+    rng = np.random.default_rng(nparts)
+    ir = (rng.standard_normal((1, cvs)) * 0.01).astype(np.float32)
+    x = rng.uniform(-1, 1, (nb, 1, pts)).astype(np.float32)
+    x2 = (rng.uniform(-1, 1, (nb, 1, pts)) * 0.01).astype(np.float32)
+    c = eng.Clpconv(0, cvs, pts)
+    assert c.get_cl_err() == 0 and c.push_ir(ir) == 0
+    y = run_stream(c, x)
+    ctv = eng.Clpconv(0, cvs, pts)
+    ytv = run_stream(ctv, x, x2)
+    o = port.pconv(cvs, pts)
+    o.push_ir(ir[0])
+    assert rel_l2(y[:, 0], np.stack([o.convolution(x[t, 0]) for t in range(nb)])) < TOL
+    o = port.pconv(cvs, pts)
+    assert rel_l2(ytv[:, 0], np.stack([o.convolution(x[t, 0], x2[t, 0]) for t in range(nb)])) < TOL
+
+
 def test_invalid_cluster_option_is_rejected_at_create(eng, options):
     options("pconv_cluster", 3)
     assert eng.Clpconv(0, 4096, 512, uData=1).get_cl_err() == 2
