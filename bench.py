@@ -480,6 +480,17 @@ def bench_latency(eng, local):
     out["dconv_4096x256x64ch_block_us"] = us
     out["dconv_4096x256x64ch_realtime_ratio"] = (256 / SR * 1e6) / us
     d.close()
+    # three corners of the reference's own benchmark grid (csound/tests.py:5-36: mono, time-varying, partition M x IR
+    # length L; the full grid: tools/rt_ratio_grid.py -> profiles/r02_rt_ratio_grid.txt)
+    grid = {}
+    for M, L in ((512, 1 << 22), (2048, 1 << 22), (8192, 1 << 20)):
+        g = eng.Clpconv(local, L, M)
+        a, b = rng.uniform(-1, 1, M).astype(np.float32), (rng.uniform(-1, 1, M) * 0.01).astype(np.float32)
+        y = np.zeros(M, np.float32)
+        us = timeit(lambda: g.convolution(y, a, b), n=100)
+        grid[f"M{M}_L{L}"] = {"block_us": us, "realtime_ratio": (M / SR * 1e6) / us}
+        g.close()
+    out["pconv_tv_mono_grid"] = grid
     return out
 
 

@@ -891,8 +891,8 @@ struct b2f_pconv {
   // general path (pts > 2^kPconvMaxLogP): batched real-FFT plans + pad / MAC / overlap-add kernels; ring positions in
   // device memory (d_state), one CUDA graph per block kind for the host call
   FftPlanCore *gfwd = nullptr, *ginv = nullptr;
-  float *d_pad = nullptr;   // [channels][2*pts]
-  float2 *d_Y = nullptr;    // [channels][pts]
+  float *d_pad = nullptr;   // [2][channels][2*pts] (second half: in2 of a time-varying block)
+  float2 *d_Y = nullptr;    // [2][channels][pts]
   float2 *d_Ypart = nullptr;  // [ksplit][channels][pts]: partial sums of a MAC whose partitions are split over CTAs
   int ksplit = 1;
   int *d_state = nullptr;   // {wp, wp2}
@@ -1133,11 +1133,11 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
     h->ginv = new (std::nothrow) FftPlanCore;
     if (!h->gfwd || !h->ginv) return fail(B2F_ERR_ALLOC);
     h->gfwd->unscaled = true;  // Clpconv's frames are never scaled (cl_conv_kernels.h:54-68)
-    if ((rc = h->gfwd->init(device, pts, 1, channels, true))) return fail(rc);
+    if ((rc = h->gfwd->init(device, pts, 1, 2 * channels, true))) return fail(rc);  // (time-varying blocks: both inputs in one batch)
     if ((rc = h->ginv->init(device, pts, 0, channels, true))) return fail(rc);
-    if ((e = cudaMalloc((void **)&h->d_pad, (size_t)channels * 2 * pts * sizeof(float))) != cudaSuccess)
+    if ((e = cudaMalloc((void **)&h->d_pad, (size_t)2 * channels * 2 * pts * sizeof(float))) != cudaSuccess)
       return fail(cuda_fail(e, "cudaMalloc pad"));
-    if ((e = cudaMalloc((void **)&h->d_Y, (size_t)channels * pts * sizeof(float2))) != cudaSuccess)
+    if ((e = cudaMalloc((void **)&h->d_Y, (size_t)2 * channels * pts * sizeof(float2))) != cudaSuccess)
       return fail(cuda_fail(e, "cudaMalloc Y"));
     {
       // enough MAC CTAs for two per SM, every CTA keeping at least 8 partitions (measured, mono, pts 8192: 512
@@ -1279,8 +1279,18 @@ static int pconv_general_step(b2f_pconv *h, bool tv, float *d_out, const float *
     rc = h->logp == 13 ? pconv_general_frames_fused_t<13>(h, tv, d_in1, d_in2, st) : pconv_general_frames_fused_t<14>(h, tv, d_in1, d_in2, st);
     if (rc) return rc;
   } else {
-    if ((rc = pconv_general_frame_state(h, d_in1, h->d_fdl, 0, st))) return rc;
-    if (tv && (rc = pconv_general_frame_state(h, d_in2, h->d_irs, 1, st))) return rc;
+    if (tv) {
+      // both inputs as ONE batch of 2 x channels transforms: pad, batched rFFT, frame stores
+      dim3 gp((2 * pts + 255) / 256, 2 * h->channels, 1);
+      pconv_pad2_kernel<<<gp, 256, 0, st>>>(d_in1, d_in2, (size_t)pts, h->d_pad, pts, h->channels);
+      CK(cudaGetLastError());
+      if ((rc = h->gfwd->run_real((const float2 *)h->d_pad, h->d_Y, 2 * h->channels, st))) return rc;
+      dim3 gs((pts / 2 + 255) / 256, 2 * h->channels, 1);
+      pconv_ring_store2_kernel<<<gs, 256, 0, st>>>(h->d_Y, h->d_fdl, h->d_irs, pts, h->nparts, h->d_state, h->channels);
+      CK(cudaGetLastError());
+    } else if ((rc = pconv_general_frame_state(h, d_in1, h->d_fdl, 0, st))) {
+      return rc;
+    }
   }
   // TMA-fed MAC by default on this path (measured 3-16 % faster with many channels, 2x for a mono 4M-tap IR);
   // option pconv_tma = 0 selects the register-fed kernel.
