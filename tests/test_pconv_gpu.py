@@ -525,6 +525,27 @@ def test_general_path_fused_launches_same_bits(eng, port, options, pts, channels
     assert rel_l2(res[1][1][:, k], np.stack([o.convolution(x[t, k], x2[t, k]) for t in range(nb)])) < TOL
 
 
+@pytest.mark.parametrize("pts", [32, 512, 8192])
+def test_push_ir_dev_with_an_odd_channel_stride(eng, pts):
+    """push_ir_dev takes any ir_stride >= the IR length: with an odd stride every second channel's rows are only 4-byte
+    aligned and the transform reads them with scalar loads. Same spectra, bit for bit, as the contiguous push (pts 32: the
+    step kernel's frame routine; 512: the register-level transform; 8192: the general path's single-launch push)."""
+    import torch
+
+    nparts, channels = 6, 3
+    cvs = nparts * pts
+    rng = np.random.default_rng(pts)
+    ir = (rng.standard_normal((channels, cvs)) * 0.05).astype(np.float32)
+    wide = np.zeros((channels, cvs + 1), np.float32)
+    wide[:, :cvs] = ir
+    a, b = eng.Clpconv(0, cvs, pts, channels=channels), eng.Clpconv(0, cvs, pts, channels=channels)
+    assert a.push_ir_dev(torch.from_numpy(ir).cuda(), cvs) == 0
+    assert b.push_ir_dev(torch.from_numpy(wide).cuda(), cvs + 1) == 0
+    torch.cuda.synchronize()
+    for k in range(channels):
+        assert np.array_equal(a.read_spectra(2, k), b.read_spectra(2, k)), k
+
+
 def test_python_binding_rejects_short_buffers(eng):
     """The C entry points read and write channels * pts floats behind the pointers they are given: the binding checks
     the element counts first (B2F_ERR_INVALID_VALUE = 2) instead of letting the engine run off the arrays."""
