@@ -51,6 +51,29 @@ for tma in (0, 1):
             assert c.convolution(y, x) == 0
             assert c.convolution(y, x, x * 0.1) == 0
 eng.set_option("pconv_tma", -1)
+# added in the last third of round 2: cluster of 16, 32 KB TMA stages (pts 2048 / 4096, >= 96 partitions per CTA), general path with
+# fused frames / inverse + overlap-add (pts 8192, 16384), partitions split over CTAs + partial sums, unfused general path
+# (pts 32768, both time-varying inputs in one batch), push_ir on the register-level transform with an odd stride
+for opts, pts, nparts, ch in (({"pconv_cluster": 16}, 512, 40, 1), ({"pconv_cluster": 2}, 2048, 200, 1), ({"pconv_cluster": 2}, 4096, 200, 1),
+                              ({}, 8192, 40, 1), ({}, 16384, 5, 2), ({"pconv_general_fused": 0}, 8192, 5, 2), ({}, 32768, 3, 1)):
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    cvs = pts * nparts
+    c = eng.Clpconv(0, cvs, pts, channels=ch)
+    assert c.get_cl_err() == 0
+    assert c.push_ir((rng.standard_normal((ch, cvs)) * 0.1).astype(np.float32)) == 0
+    y = np.zeros((ch, pts), np.float32)
+    for t in range(3):
+        x = rng.uniform(-1, 1, (ch, pts)).astype(np.float32)
+        assert c.convolution(y, x) == 0
+        assert c.convolution(y, x, x * 0.1) == 0
+    for k in opts:
+        eng.set_option(k, {"pconv_cluster": 0, "pconv_general_fused": 1}[k])
+import torch  # noqa: E402
+
+cw = eng.Clpconv(0, 6 * 512, 512, channels=3)
+assert cw.push_ir_dev(torch.randn(3, 6 * 512 + 1, device="cuda"), 6 * 512 + 1) == 0
+torch.cuda.synchronize()
 # direct convolution: single block (cluster tap split), multi-block (16 outputs per thread), ragged sizes, time-varying
 for irsize, vsize, ch, nb in ((4096, 256, 2, 1), (4096, 256, 2, 6), (100, 16, 3, 1), (64, 1, 2, 3)):
     d = eng.Cldconv(0, irsize, vsize, channels=ch, max_blocks=nb)
