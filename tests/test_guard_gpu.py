@@ -78,6 +78,31 @@ def test_pconv_device_entry_points_stay_in_bounds(eng, pts, nparts, channels):
     assert torch.isfinite(y.view).all() and not (y.view == SENT).any()
 
 
+@pytest.mark.parametrize("opts,pts,nparts,channels", [({"pconv_cluster": 16}, 512, 40, 1), ({"pconv_cluster": 2}, 2048, 200, 2),
+                                                      ({"pconv_cluster": 2}, 4096, 200, 1), ({}, 8192, 40, 1), ({}, 16384, 5, 3),
+                                                      ({"pconv_general_fused": 0}, 8192, 5, 3), ({}, 32768, 3, 2)])
+def test_pconv_few_channel_paths_stay_in_bounds(eng, options, opts, pts, nparts, channels):
+    """The launch shapes added for a few channels with long IRs: cluster of 16, 32 KB TMA stages, general path with the
+    partitions split over CTAs, fused frames / inverse + overlap-add, both time-varying inputs in one batch."""
+    for k, v in opts.items():
+        options(k, v)
+    cvs = pts * nparts + 5
+    c = eng.Clpconv(0, cvs, pts, channels=channels)
+    assert c.get_cl_err() == 0
+    ir = Guarded(channels * cvs)
+    ir.view.normal_(0, 0.1)
+    assert c.push_ir_dev(ir.view, cvs) == 0
+    x, x2, y = Guarded(channels * pts), Guarded(channels * pts), Guarded(channels * pts)
+    x.view.uniform_(-1, 1)
+    x2.view.uniform_(-0.1, 0.1)
+    for t in range(4):
+        assert c.convolution_dev(y.view, x.view) == 0
+        assert c.convolution_dev(y.view, x.view, x2.view) == 0
+    torch.cuda.synchronize()
+    assert ir.intact() and x.intact() and x2.intact() and y.intact()
+    assert torch.isfinite(y.view).all() and not (y.view == SENT).any()
+
+
 @pytest.mark.parametrize("irsize,vsize,channels,nblocks", [(4096, 256, 3, 1), (4096, 256, 3, 7), (100, 16, 5, 3), (33, 1, 2, 5), (512, 64, 300, 1)])
 def test_dconv_device_entry_points_stay_in_bounds(eng, irsize, vsize, channels, nblocks):
     d = eng.Cldconv(0, irsize, vsize, channels=channels)
