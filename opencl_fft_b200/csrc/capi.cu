@@ -66,6 +66,7 @@ extern "C" const char *b2f_version(void) { return "b200fft 0.1 (sm_100a)"; }
 // b2f_set_option() changes them for handles created later (include/b200fft.h lists the names).
 struct Options {
   long long fft_sm_min_batch = 96;   // N = 2^15: one-SM kernel from this batch up (0: never, 1: always)
+  long long fft_sm_8192 = 1;         // complex N = 8192 on the one-SM kernel too (four transforms per unit), from 4 x fft_sm_min_batch
   long long large_chunk_mb = 256;    // scratch chunk of the four-step launch pair
   long long rows_rb16 = 0;           // 16-row CTAs in the real rows kernel
   long long separate_split = 0;      // unfused real split / unsplit pass (four-step path)
@@ -89,6 +90,7 @@ struct OptionName {
 };
 static const OptionName kOptionNames[] = {
     {"fft_sm_min_batch", "B2F_FFT_SM_MIN_BATCH", &Options::fft_sm_min_batch},
+    {"fft_sm_8192", "B2F_FFT_SM_8192", &Options::fft_sm_8192},
     {"large_chunk_mb", "B2F_LARGE_CHUNK_MB", &Options::large_chunk_mb},
     {"rows_rb16", "B2F_ROWS_RB16", &Options::rows_rb16},
     {"separate_split", "B2F_SEPARATE_SPLIT", &Options::separate_split},
@@ -405,7 +407,7 @@ struct SmPlan {
   // spreads every transform over the whole GPU, is the faster one (measured crossover, tools/fft_sm_probe.py).
   // N = 2^14 runs two transforms per CTA iteration: twice the batch before the GPU is full.
   long long min_batch = 96;
-  bool use_for(int batch) const { return ok() && min_batch > 0 && batch >= min_batch * (logn == 14 ? 2 : 1); }
+  bool use_for(int batch) const { return ok() && min_batch > 0 && batch >= min_batch * (32 >> (logn - 10)); }
   int init(int device, int logn_) {
     logn = logn_;
     const int N = 1 << logn;
@@ -458,6 +460,9 @@ struct SmPlan {
   template <bool INV, int KIND>
   int run(const float2 *in, float2 *out, const float2 *hw, int batch, float scale, cudaStream_t st) {
     if (logn == 14) return run_t<INV, KIND, 4>(in, out, hw, batch, scale, st);
+    if constexpr (KIND == kSmComplex) {
+      if (logn == 13) return run_t<INV, KIND, 3>(in, out, hw, batch, scale, st);  // (complex only: init() leaves real plans of 2^13 alone)
+    }
     return run_t<INV, KIND, 5>(in, out, hw, batch, scale, st);
   }
 };
@@ -663,7 +668,7 @@ struct FftPlanCore {
       rc = upload(make_pass_twiddles(logn), &d_tw);
       if (rc) return rc;
     }
-    if ((logn == SmGeom::LOGN || logn == 14) && opt.fft_sm_min_batch > 0) {
+    if ((logn == SmGeom::LOGN || logn == 14 || (logn == 13 && !real && opt.fft_sm_8192)) && opt.fft_sm_min_batch > 0) {
       sm.min_batch = opt.fft_sm_min_batch;
       rc = sm.init(dev, logn);
       if (rc) return rc;

@@ -91,6 +91,20 @@ __device__ __forceinline__ void dft16x2(float2 (&v)[32]) {
   }
 }
 
+// four independent 8-point butterflies (N = 2^13: four transforms per unit)
+template <bool INV>
+__device__ __forceinline__ void dft8x4(float2 (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    float2 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = v[8 * g + i];
+    dft8<INV>(a);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[8 * g + i] = a[i];
+  }
+}
+
 // ---- tensor memory as a scratch-pad -----------------------------------------------------------------------------
 // 32x32b shape: lane i of the issuing warp reads / writes 32-bit columns [col, col + n) of TMEM lane 32 (warp % 4) + i,
 // i.e. storage private to the thread. Address = (lane << 16) | column.
@@ -209,7 +223,8 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   using G = SmGeom;
   constexpr bool REAL = (KIND == kSmRealFwd), C2R = (KIND == kSmRealInv);
   static_assert(!(REAL && INV) && !(C2R && !INV), "the split follows a forward, the unsplit precedes an inverse transform");
-  static_assert(LOG1 == 5 || LOG1 == 4, "N = 2^15, or two transforms of 2^14 per unit");
+  static_assert(LOG1 == 5 || LOG1 == 4 || LOG1 == 3, "N = 2^15, two transforms of 2^14 or four of 2^13 per unit");
+  static_assert(LOG1 != 3 || KIND == kSmComplex, "N = 2^13: complex transforms only");
   constexpr int N1 = 1 << LOG1, NTR = 32 / N1;  // radix of P1, transforms per unit
   constexpr int N = N1 * 1024;
   const int units = (batch + NTR - 1) / NTR;
@@ -367,10 +382,16 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
       if constexpr (LOG1 == 5) {
         B2F_SMX_FFT(dft32<INV>(v));
         B2F_SMX_FFT((tw_tree<4, 0, false>(v, make_float2(1.f, 0.f), base)));
-      } else {
+      } else if constexpr (LOG1 == 4) {
         B2F_SMX_FFT(dft16x2<INV>(v));
         B2F_SMX_FFT((tw_tree<3, 0, false, 0>(v, make_float2(1.f, 0.f), base)));
         B2F_SMX_FFT((tw_tree<3, 0, false, 16>(v, make_float2(1.f, 0.f), base)));
+      } else {
+        B2F_SMX_FFT(dft8x4<INV>(v));
+        B2F_SMX_FFT((tw_tree<2, 0, false, 0>(v, make_float2(1.f, 0.f), base)));
+        B2F_SMX_FFT((tw_tree<2, 0, false, 8>(v, make_float2(1.f, 0.f), base)));
+        B2F_SMX_FFT((tw_tree<2, 0, false, 16>(v, make_float2(1.f, 0.f), base)));
+        B2F_SMX_FFT((tw_tree<2, 0, false, 24>(v, make_float2(1.f, 0.f), base)));
       }
 #pragma unroll
       for (int s = 0; s < 16; s++) *reinterpret_cast<float2 *>(rows + s * G::ROW + pos * 8) = v[s];
@@ -448,7 +469,9 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
         const bool mirrored = REAL && LOG1 == 5 && job == 0;
         const int slot = mirrored ? ((16 - s) & 15) : s;
         const int k2 = (h != (int)mirrored) ? 31 - warp : warp;
-        const int k1 = LOG1 == 5 ? 16 * job + slot : slot;  // LOG1 = 4: job = transform of the unit, rows 0..15 each
+        // LOG1 = 4: job = transform of the unit, rows 0..15 each; LOG1 = 3: two transforms per job, rows 0..7 each
+        const int k1 = LOG1 == 5 ? 16 * job + slot : (LOG1 == 4 ? slot : (slot & 7));
+        const int trj = LOG1 == 5 ? 0 : (LOG1 == 4 ? job : 2 * job + (slot >> 3));  // transform of the unit
         const unsigned char *p = rows + slot * G::ROW + k2 * G::K2S;
         float2 v[32];
 #pragma unroll
@@ -467,9 +490,9 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
           __syncwarp();
         }
         B2F_SMX_FFT(dft32<INV>(v));
-        float2 *o = dst + (LOG1 == 5 ? 0 : (size_t)job * N) + k1 + N1 * k2;
+        float2 *o = dst + (size_t)trj * N + k1 + N1 * k2;
         if constexpr (!REAL) {
-          if (LOG1 == 5 || t * NTR + job < batch) {  // (the second transform of the last unit of an odd batch)
+          if (LOG1 == 5 || t * NTR + trj < batch) {  // (the last unit of a batch that is not a multiple of NTR)
 #pragma unroll
             for (int k3 = 0; k3 < 32; k3++) B2F_SMX_STG(o[32 * N1 * k3], cscale(v[k3], scale));
           }

@@ -293,6 +293,38 @@ def test_one_sm_kernel_16384_point_complex(eng, options, batch):
     assert rel_l2(got[1, True], got[0, True]) < 1e-6 and rel_l2(got[1, False], got[0, False]) < 1e-6
 
 
+@pytest.mark.parametrize("batch", [1, 3, 4, 5, 590, 593, 600])
+def test_one_sm_kernel_8192_point_complex(eng, options, batch):
+    """N = 2^13 on the one-SM kernel: FOUR transforms per unit of work (two per job, rows 0..7 each; the second job
+    parked in tensor memory), so batches that are not multiples of four end in a partly empty unit and 593+ make CTAs
+    loop. Every transform, forward and inverse, against float64; in place equals out of place; and the default selection
+    for small batches (cfft_kernel<13>) agrees to rounding."""
+    import torch
+
+    N = 8192
+    rng = np.random.default_rng(batch)
+    z = crand(rng, batch, N)
+    zz = z.astype(np.complex128)
+    got = {}
+    for forced in (1, 0):
+        options("fft_sm_min_batch", forced)
+        for fwd in (True, False):
+            p = eng.Clcfft(0, N, fwd, max_batch=batch)
+            y = z.copy()
+            assert p.transform(y.reshape(-1)) == 0
+            truth = np.fft.fft(zz, axis=1) / N if fwd else np.fft.ifft(zz, axis=1) * N
+            err = np.linalg.norm(y - truth, axis=1) / np.linalg.norm(truth, axis=1)
+            assert err.max() < 2e-6, (forced, fwd, int(err.argmax()), float(err.max()))
+            got[forced, fwd] = y
+            if forced and fwd:
+                d = torch.from_numpy(z.view(np.float32).copy()).cuda()
+                o = torch.empty_like(d)
+                assert p.transform_dev(d, o, batch) == 0 and p.transform_dev(d, d, batch) == 0
+                torch.cuda.synchronize()
+                assert torch.equal(d, o) and np.array_equal(o.cpu().numpy().view(np.complex64), y)
+    assert rel_l2(got[1, True], got[0, True]) < 1e-6 and rel_l2(got[1, False], got[0, False]) < 1e-6
+
+
 @pytest.mark.parametrize("batch", [1, 2, 3, 149, 297, 300])
 def test_one_sm_kernel_32768_point_real(eng, port, options, batch):
     """The 32768-point real transform (N = 2^14 complex) on the one-SM kernel: the split pairs lanes of one warp inside a

@@ -103,6 +103,25 @@ def test_pconv_few_channel_paths_stay_in_bounds(eng, options, opts, pts, nparts,
     assert torch.isfinite(y.view).all() and not (y.view == SENT).any()
 
 
+@pytest.mark.parametrize("batch", [5, 593])
+def test_one_sm_fft_8192_stays_in_bounds(eng, options, batch):
+    """Complex N = 8192 on the one-SM kernel (four transforms per unit): a last unit with one transform in it."""
+    options("fft_sm_min_batch", 1)
+    n = 8192
+    for fwd in (True, False):
+        plan = eng.Clcfft(0, n, fwd, max_batch=batch)
+        assert plan.get_error() == 0
+        src, dst = Guarded(batch * n * 2), Guarded(batch * n * 2)
+        src.view.uniform_(-1, 1)
+        assert plan.transform_dev(src.view, dst.view, batch) == 0
+        torch.cuda.synchronize()
+        assert src.intact() and dst.intact()
+        assert torch.isfinite(dst.view).all() and not (dst.view == SENT).any()
+        assert plan.transform_dev(src.view, src.view, batch) == 0  # in place
+        torch.cuda.synchronize()
+        assert src.intact()
+
+
 @pytest.mark.parametrize("irsize,vsize,channels,nblocks", [(4096, 256, 3, 1), (4096, 256, 3, 7), (100, 16, 5, 3), (33, 1, 2, 5), (512, 64, 300, 1)])
 def test_dconv_device_entry_points_stay_in_bounds(eng, irsize, vsize, channels, nblocks):
     d = eng.Cldconv(0, irsize, vsize, channels=channels)
