@@ -62,8 +62,8 @@ const char *b2f_version(void);
  *   fft_sm_min_batch  96     N = 32768 complex / 65536 real: the one-SM kernel from this batch up
  *                            (0 never, 1 always); below it the four-step launch pair. N = 16384 / 32768 real:
  *                            from twice this batch up (two transforms per CTA iteration); below, one CTA each
- *   fft_sm_8192       1      complex N = 8192 on the one-SM kernel as well (four transforms per CTA iteration), from
- *                            four times fft_sm_min_batch; 0: cfft_kernel<13> at every batch
+ *   fft_sm_8192       1      complex N = 8192 and the inverse 16384-point real transform on the one-SM kernel as well
+ *                            (four transforms per CTA iteration), from four times fft_sm_min_batch; 0: one CTA each
  *   large_chunk_mb    256    scratch chunk of the four-step launch pair
  *   rows_rb16         0      16-row CTAs in the four-step real rows kernel
  *   separate_split    0      unfused real split / unsplit pass on the four-step path

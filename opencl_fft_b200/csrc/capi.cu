@@ -66,7 +66,7 @@ extern "C" const char *b2f_version(void) { return "b200fft 0.1 (sm_100a)"; }
 // b2f_set_option() changes them for handles created later (include/b200fft.h lists the names).
 struct Options {
   long long fft_sm_min_batch = 96;   // N = 2^15: one-SM kernel from this batch up (0: never, 1: always)
-  long long fft_sm_8192 = 1;         // complex N = 8192 on the one-SM kernel too (four transforms per unit), from 4 x fft_sm_min_batch
+  long long fft_sm_8192 = 1;         // complex N = 8192 and inverse real 16384 on the one-SM kernel too (four transforms per unit), from 4 x fft_sm_min_batch
   long long large_chunk_mb = 256;    // scratch chunk of the four-step launch pair
   long long rows_rb16 = 0;           // 16-row CTAs in the real rows kernel
   long long separate_split = 0;      // unfused real split / unsplit pass (four-step path)
@@ -460,8 +460,8 @@ struct SmPlan {
   template <bool INV, int KIND>
   int run(const float2 *in, float2 *out, const float2 *hw, int batch, float scale, cudaStream_t st) {
     if (logn == 14) return run_t<INV, KIND, 4>(in, out, hw, batch, scale, st);
-    if constexpr (KIND == kSmComplex) {
-      if (logn == 13) return run_t<INV, KIND, 3>(in, out, hw, batch, scale, st);  // (complex only: init() leaves real plans of 2^13 alone)
+    if constexpr (KIND != kSmRealFwd) {
+      if (logn == 13) return run_t<INV, KIND, 3>(in, out, hw, batch, scale, st);  // (init() leaves forward real plans of 2^13 alone)
     }
     return run_t<INV, KIND, 5>(in, out, hw, batch, scale, st);
   }
@@ -668,7 +668,7 @@ struct FftPlanCore {
       rc = upload(make_pass_twiddles(logn), &d_tw);
       if (rc) return rc;
     }
-    if ((logn == SmGeom::LOGN || logn == 14 || (logn == 13 && !real && opt.fft_sm_8192)) && opt.fft_sm_min_batch > 0) {
+    if ((logn == SmGeom::LOGN || logn == 14 || (logn == 13 && (!real || !fwd) && opt.fft_sm_8192)) && opt.fft_sm_min_batch > 0) {
       sm.min_batch = opt.fft_sm_min_batch;
       rc = sm.init(dev, logn);
       if (rc) return rc;

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(SmGeom::THREADS, 1)
   constexpr bool REAL = (KIND == kSmRealFwd), C2R = (KIND == kSmRealInv);
   static_assert(!(REAL && INV) && !(C2R && !INV), "the split follows a forward, the unsplit precedes an inverse transform");
   static_assert(LOG1 == 5 || LOG1 == 4 || LOG1 == 3, "N = 2^15, two transforms of 2^14 or four of 2^13 per unit");
-  static_assert(LOG1 != 3 || KIND == kSmComplex, "N = 2^13: complex transforms only");
+  static_assert(LOG1 != 3 || KIND != kSmRealFwd, "N = 2^13: complex and inverse real transforms only");
   constexpr int N1 = 1 << LOG1, NTR = 32 / N1;  // radix of P1, transforms per unit
   constexpr int N = N1 * 1024;
   const int units = (batch + NTR - 1) / NTR;

@@ -325,6 +325,33 @@ def test_one_sm_kernel_8192_point_complex(eng, options, batch):
     assert rel_l2(got[1, True], got[0, True]) < 1e-6 and rel_l2(got[1, False], got[0, False]) < 1e-6
 
 
+@pytest.mark.parametrize("batch", [4, 5, 7, 593, 600])
+def test_one_sm_kernel_16384_point_inverse_real(eng, port, options, batch):
+    """The inverse 16384-point real transform (N = 2^13 complex) on the one-SM kernel, four transforms per unit: the
+    unsplit pairs staged runs j1 <-> 7 - j1 of the same transform. Every transform against the one-CTA kernel (to
+    rounding), the oracle for two of them, and the round trip through the forward transform."""
+    size = 16384
+    rng = np.random.default_rng(batch)
+    x = rng.uniform(-1, 1, (batch, size)).astype(np.float32)
+    options("fft_sm_min_batch", 0)
+    spec = np.zeros((batch, size // 2), np.complex64)
+    assert eng.Clrfft(0, size, True, max_batch=batch).transform(spec.reshape(-1), x.reshape(-1).copy()) == 0
+    got = {}
+    for forced in (1, 0):
+        options("fft_sm_min_batch", forced)
+        iv = eng.Clrfft(0, size, False, max_batch=batch)
+        c, r = spec.copy(), np.zeros((batch, size), np.float32)
+        assert iv.transform(c.reshape(-1), r.reshape(-1)) == 0
+        got[forced] = r
+    err = np.linalg.norm(got[1] - got[0], axis=1) / np.linalg.norm(got[0], axis=1)
+    assert err.max() < 1e-6, (int(err.argmax()), float(err.max()))
+    assert not np.array_equal(got[1], got[0])  # (the forced plan really took the other kernel)
+    back = np.linalg.norm(got[1] - x, axis=1) / np.linalg.norm(x, axis=1)
+    assert back.max() < 2e-6
+    for k in (0, batch - 1):
+        assert rel_l2(got[1][k], port.rfft_inv(spec[k])) < 1e-6
+
+
 @pytest.mark.parametrize("batch", [1, 2, 3, 149, 297, 300])
 def test_one_sm_kernel_32768_point_real(eng, port, options, batch):
     """The 32768-point real transform (N = 2^14 complex) on the one-SM kernel: the split pairs lanes of one warp inside a

@@ -108,8 +108,8 @@ def test_one_sm_fft_8192_stays_in_bounds(eng, options, batch):
     """Complex N = 8192 on the one-SM kernel (four transforms per unit): a last unit with one transform in it."""
     options("fft_sm_min_batch", 1)
     n = 8192
-    for fwd in (True, False):
-        plan = eng.Clcfft(0, n, fwd, max_batch=batch)
+    for fwd in (True, False, None):  # None: the inverse 16384-point real transform, on the same kernel
+        plan = eng.Clcfft(0, n, fwd, max_batch=batch) if fwd is not None else eng.Clrfft(0, 2 * n, False, max_batch=batch)
         assert plan.get_error() == 0
         src, dst = Guarded(batch * n * 2), Guarded(batch * n * 2)
         src.view.uniform_(-1, 1)
