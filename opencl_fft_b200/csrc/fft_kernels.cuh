@@ -13,6 +13,10 @@
 #include "fft_core.cuh"
 #include "tma_utils.cuh"
 
+#ifndef B2F_SPLIT_SHFL
+#define B2F_SPLIT_SHFL 1
+#endif
+
 namespace b2f {
 
 // threads per CTA we aim for when several small transforms share a CTA
@@ -130,12 +134,26 @@ __device__ __forceinline__ void rfft_fwd_reg_body(const float2 *src, float2 *dst
   };
   auto store = [&](int, float2 v, int slot) { x[slot] = v; };  // last pass: slot == m, value X[t + m*T]
   fft_run<LOGN, false>(load, store, sm, tw, t, CtaSync());
-  __syncthreads();  // every thread is past its last gather: sm becomes the staging area [E/2][T]
-#pragma unroll
-  for (int m = H; m < E; m++) sm[(m - H) * T + t] = x[m];
-  __syncthreads();
-  if (!active) return;
   const int pt = (t == 0) ? 0 : T - t;  // partner thread (itself for t = 0 and t = T/2)
+  // T <= 32 (N <= 512): the partner sits in the same warp -- its high members arrive by shuffle (no staging in shared
+  // memory, no CTA barriers; B2F_SPLIT_SHFL=0 keeps the staged exchange for comparison)
+  constexpr bool SHFL = B2F_SPLIT_SHFL && T <= 32;
+  float2 ph[H];  // ph[m]: the partner's value X[pt + pm * T], pm = E - 1 - m (E - m for t = 0: the thread's own)
+  if constexpr (SHFL) {
+    const int plane = ((int)threadIdx.x & 31 & ~(T - 1)) | pt;
+#pragma unroll
+    for (int m = 0; m < H; m++) {
+      ph[m].x = __shfl_sync(0xffffffffu, x[E - 1 - m].x, plane);
+      ph[m].y = __shfl_sync(0xffffffffu, x[E - 1 - m].y, plane);
+      if (t == 0 && m > 0) ph[m] = x[E - m];
+    }
+  } else {
+    __syncthreads();  // every thread is past its last gather: sm becomes the staging area [E/2][T]
+#pragma unroll
+    for (int m = H; m < E; m++) sm[(m - H) * T + t] = x[m];
+    __syncthreads();
+  }
+  if (!active) return;
   const float hs = 0.5f * scale;
   // measured: deriving the split twiddles pays up to N = 4096 (r2c 4096: 89 -> 92 % of the HBM peak); above, the
   // 512- and 1024-thread CTAs are bound by their phases, not by the LSU pipe, and the table loads are faster
@@ -149,7 +167,8 @@ __device__ __forceinline__ void rfft_fwd_reg_body(const float2 *src, float2 *dst
       continue;
     }
     const int pm = (t == 0) ? E - m : E - 1 - m;
-    float2 a = x[m], bb = sm[(pm - H) * T + pt];
+    float2 a = x[m], bb;
+    if constexpr (SHFL) bb = ph[m]; else bb = sm[(pm - H) * T + pt];
     rfft_pair_folded<false>(a, bb, DERIVE ? split_tw<false, E>(hw0, m) : __ldg(&hw[t + m * T]), hs);
     __stcs(dst + t + m * T, a);
     __stcs(dst + pt + pm * T, bb);
@@ -200,16 +219,28 @@ __device__ __forceinline__ void rfft_inv_reg_body(const float2 *src, float2 *dst
     rfft_pair_folded<true>(x[m], hi[m], __ldg(&hw[t + m * T]), 0.5f);  // (derived twiddles measured slower here)
   }
   // the one exchange: hand the high members to their owners
+  if constexpr (B2F_SPLIT_SHFL && T <= 32) {
+    // the owner is in the same warp: slot m' of thread t is hi[E - 1 - m'] of its partner (t = 0 keeps its own: slot
+    // E/2 is element N/2 = hi[0], slot m' is hi[E - m'])
+    const int plane = ((int)threadIdx.x & 31 & ~(T - 1)) | pt;
 #pragma unroll
-  for (int m = 0; m < H; m++) {
-    const int pm = (t == 0) ? ((E - m) & (E - 1)) : E - 1 - m;  // (t = 0, m = 0) parks element N/2 in slot E/2
-    const int slot = (t == 0 && m == 0) ? H : pm;
-    sm[(slot - H) * T + pt] = hi[m];
+    for (int m = H; m < E; m++) {
+      x[m].x = __shfl_sync(0xffffffffu, hi[E - 1 - m].x, plane);
+      x[m].y = __shfl_sync(0xffffffffu, hi[E - 1 - m].y, plane);
+      if (t == 0) x[m] = hi[(E - m) & (H - 1)];  // m = H -> hi[0]; m > H -> hi[E - m]
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < H; m++) {
+      const int pm = (t == 0) ? ((E - m) & (E - 1)) : E - 1 - m;  // (t = 0, m = 0) parks element N/2 in slot E/2
+      const int slot = (t == 0 && m == 0) ? H : pm;
+      sm[(slot - H) * T + pt] = hi[m];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = H; m < E; m++) x[m] = sm[(m - H) * T + t];
+    __syncthreads();  // staging is the engine's work buffer from here on
   }
-  __syncthreads();
-#pragma unroll
-  for (int m = H; m < E; m++) x[m] = sm[(m - H) * T + t];
-  __syncthreads();  // staging is the engine's work buffer from here on
   // first pass: value index m of (idx, slot): idx = (t + q*T) + r*(N/R0), slot = q*R0 + r  ->  m = q + r*(E/R0)
   auto load = [&](int, int slot) { return x[(slot / R0) + (slot % R0) * (E / R0)]; };
   if constexpr (!OLA) {
