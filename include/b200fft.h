@@ -79,7 +79,7 @@ const char *b2f_version(void);
  *   fft_prefetch      -1     real transforms of 8192 / 16384 complex points, one CTA each: L2 prefetch of the
  *                            transform this many CTAs ahead (-1: the co-resident CTAs, 0: off)
  *   pconv_cluster16_max_channels 4  clusters of 16 CTAs (non-portable size) for handles of up to this many channels
- *                            (twice as many at pts <= 1024)
+ *                            (four times as many at pts <= 1024)
  *                            and at least 8 MB of rings per channel; 0 never
  *   pconv_deep_ring   1      handles whose launches put at most one CTA on an SM and whose CTAs stream >= 96 partitions
  *                            of 2048 / 4096 samples each (mono, long IR): TMA stages of 32 KB; 0: the usual 4 KB slices

@@ -1101,10 +1101,13 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   // at a time) halves it once more.
   // Measured, mono (tools/rt_ratio_grid.py): pts 512 x 8192 partitions 147 -> 82 us per block, pts 2048 x 2048: 256 -> 136;
   // nothing to gain below ~8 MB of rings per channel (pts 512 x 1024: 31.0 vs 29.5 us).
-  // Up to twice as many channels at pts <= 1024 (register feed; 8 channels x 8192 partitions of 512: 198 -> 109 us; 8 channels
-  // x 2048 of 2048: 121 us with 8 CTAs per cluster, 139 with 16; tools/pconv_cluster16_probe.py).
-  const long long max16 = h->opt.pconv_cluster16_max_channels * (pts <= 1024 ? 2 : 1);
-  if (S == 8 && channels <= max16 && (long long)h->nparts * pts >= (1 << 19) && h->nparts >= 64) S = 16;
+  // More channels at pts <= 1024 (register feed; 8 channels x 8192 partitions of 512: 198 -> 109 us; 8 channels x 2048 of
+  // 2048: 121 us with 8 CTAs per cluster, 139 with 16; tools/pconv_cluster16_probe.py).
+  // 16 channels x 937 partitions of 512: 30.2 -> 25.1 us, x 468 of 1024: 39.2 -> 31.0; 32 channels: 41 -> 54 us, so four times
+  // the channel limit at pts <= 1024 and no further (tools/pconv_cluster16_probe2.py).
+  const bool small = pts <= 1024;
+  const long long max16 = h->opt.pconv_cluster16_max_channels * (small ? 4 : 1);
+  if (S == 8 && channels <= max16 && (long long)h->nparts * pts >= (small ? (1 << 18) : (1 << 19)) && h->nparts >= 64) S = 16;
   auto fail = [&](int code) {
     h->destroy();
     delete h;
