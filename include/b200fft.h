@@ -81,8 +81,9 @@ const char *b2f_version(void);
  *   pconv_cluster16_max_channels 4  clusters of 16 CTAs (non-portable size) for handles of up to this many channels
  *                            (four times as many at pts <= 1024)
  *                            and at least 8 MB of rings per channel; 0 never
- *   pconv_deep_ring   1      handles whose launches put at most one CTA on an SM and whose CTAs stream >= 96 partitions
- *                            of 2048 / 4096 samples each (mono, long IR): TMA stages of 32 KB; 0: the usual 4 KB slices
+ *   pconv_deep_ring   1      handles whose launches put at most one CTA on an SM (mono and few-channel streams of 2048 /
+ *                            4096-sample partitions): TMA stages of 32 KB; 0: the usual 4 KB slices
+ *   pconv_deep_min_parts 16  ... when a CTA streams at least this many partitions
  *   pconv_ksplit      0      pts >= 8192 with few channels: the partitions of the spectral multiply-accumulate are split
  *                            over this many CTAs per 512-bin tile and the partial sums added by a second launch
  *                            (0: enough for two CTAs per SM, -1: never)

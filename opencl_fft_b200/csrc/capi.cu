@@ -78,9 +78,10 @@ struct Options {
   long long pinned_direct = 1;       // pconv host calls on caller-pinned buffers: the kernel reads / writes them in place
   long long fft_prefetch = -1;       // real one-CTA transforms of N >= 8192: L2 prefetch distance in CTAs (-1: the resident CTAs, 0: off)
   long long pconv_cluster16_max_channels = 4;  // clusters of 16 CTAs for up to this many channels with long IRs (0: never)
-  long long pconv_deep_ring = 1;     // launches of at most one CTA per SM streaming >= 96 partitions each (pts 2048 / 4096): TMA stages of 32 KB
+  long long pconv_deep_ring = 1;     // launches of at most one CTA per SM (pts 2048 / 4096): TMA stages of 32 KB
   long long pconv_ksplit = 0;        // general path (pts >= 8192): partitions split over this many CTAs per tile (0: measured choice, -1: never)
   long long pconv_general_fused = 1; // pts 8192 / 16384: frames and inverse + overlap-add as fused launches (0: pad / rFFT / copy / ... one by one)
+  long long pconv_deep_min_parts = 16;  // ... from this many partitions per CTA (measured: mono pts 2048 x 1024 partitions 65.9 -> 31.0 us, x 512: 39.2 -> 22.7)
   long long pconv_push_reg = 1;      // push_ir on the register-level real transform (pts >= 64); 0: the step kernel's frame routine
   long long verbose = 0;
 };
@@ -105,6 +106,7 @@ static const OptionName kOptionNames[] = {
     {"pconv_deep_ring", "B2F_PCONV_DEEP_RING", &Options::pconv_deep_ring},
     {"pconv_ksplit", "B2F_PCONV_KSPLIT", &Options::pconv_ksplit},
     {"pconv_general_fused", "B2F_PCONV_GENERAL_FUSED", &Options::pconv_general_fused},
+    {"pconv_deep_min_parts", "B2F_PCONV_DEEP_MIN_PARTS", &Options::pconv_deep_min_parts},
     {"pconv_push_reg", "B2F_PCONV_PUSH_REG", &Options::pconv_push_reg},
     {"verbose", "B2F_VERBOSE", &Options::verbose},
 };
@@ -1120,13 +1122,13 @@ extern "C" int b2f_pconv_create(b2f_pconv **out, int device, int cvs, int pts, i
   }
   h->cluster = S;
   // Measured (tools/pconv_few_channels_probe.py, profiles/r02_pconv_few_channels.txt): mono, pts 2048 x 2048 partitions
-  // 121 -> 55 us per block; no gain or a loss when a CTA streams only a few dozen partitions (16 channels x 234: 45.4 vs
-  // 46.5 us) and at pts 1024 (register feed: 19.6 vs 24.8 us)
-  h->deep = h->opt.pconv_deep_ring != 0 && logp >= 11 && (long long)channels * S <= sm_count() && h->nparts / S >= 96;
+  // 121 -> 55 us per block, x 1024: 65.9 -> 31.0, x 512: 39.2 -> 22.7 (tools/pconv_deep_threshold_probe.py); nothing to gain at
+  // 16 channels x 234 (45.3 vs 43.8 us); a loss at pts 1024 (register feed: 19.6 vs 24.8 us)
+  h->deep = h->opt.pconv_deep_ring != 0 && logp >= 11 && (long long)channels * S <= sm_count() && h->nparts / S >= h->opt.pconv_deep_min_parts;
   if (S == 16 && !h->opt.pconv_cluster && logp <= kPconvMaxLogP && pconv_cluster_fits(logp, 16, (int)h->opt.pconv_tma, h->deep) != 1) {
     // this device cannot co-schedule 16 such CTAs: the portable limit it is
     S = h->cluster = 8;
-    h->deep = h->opt.pconv_deep_ring != 0 && logp >= 11 && (long long)channels * S <= sm_count() && h->nparts / S >= 96;
+    h->deep = h->opt.pconv_deep_ring != 0 && logp >= 11 && (long long)channels * S <= sm_count() && h->nparts / S >= h->opt.pconv_deep_min_parts;
   }
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "stream"));
